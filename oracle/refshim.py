@@ -1,0 +1,139 @@
+"""Import shim for the REAL sisl/MADRL reference classes (test infrastructure only).
+
+TEST INFRASTRUCTURE -- never imported by the product package ``madrl_b200``.
+
+The reference (``/root/reference``) is pure Python but cannot be imported unmodified on this
+image: ``rltools/rltools/util.py`` is a SyntaxError on Python >= 3.7 and ``gym`` / ``matplotlib``
+are not installed.  This module registers *stub modules* for exactly those
+imports in ``sys.modules`` and puts the reference root on ``sys.path`` so that
+
+    madrl_environments.pursuit.waterworld.MAWaterWorld
+    madrl_environments.pursuit.pursuit_evade.PursuitEvade
+    madrl_environments.hostage.ContinuousHostageWorld
+
+can be imported and executed UNMODIFIED.  No reference file is copied or edited.  The reference
+only exists in the build container, so everything that uses this shim (``oracle/make_golden.py``
+and the ``reference``-marked tests) is skipped automatically when ``/root/reference`` is absent
+(e.g. on the GPU box); what travels are the golden vectors it produced (``tests/golden``).
+
+Stub behaviour follows the originals:
+  * ``rltools.util.EzPickle``      -- pickle by constructor args (rltools/rltools/util.py:261-288)
+  * ``rltools.util.stack_dict_list`` -- (rltools/rltools/util.py:125-138)
+  * ``gym.spaces.Box/Discrete``    -- shape/low/high/n holders
+  * ``gym.utils.seeding.np_random``-- returns (numpy RandomState, seed)
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("MADRL_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "madrl_environments"))
+
+
+class _EzPickle(object):
+    def __init__(self, *args, **kwargs):
+        self._ezpickle_args = args
+        self._ezpickle_kwargs = kwargs
+
+    def __getstate__(self):
+        return {"_ezpickle_args": self._ezpickle_args, "_ezpickle_kwargs": self._ezpickle_kwargs}
+
+    def __setstate__(self, d):
+        out = type(self)(*d["_ezpickle_args"], **d["_ezpickle_kwargs"])
+        self.__dict__.update(out.__dict__)
+
+
+def _stack_dict_list(dict_list):
+    ret = dict()
+    if not dict_list:
+        return ret
+    for k in dict_list[0].keys():
+        eg = dict_list[0][k]
+        if isinstance(eg, dict):
+            ret[k] = _stack_dict_list([x[k] for x in dict_list])
+        else:
+            ret[k] = np.array([x[k] for x in dict_list])
+    return ret
+
+
+class _Box(object):
+    def __init__(self, low, high, shape=None):
+        if shape is None:
+            self.low = np.asarray(low, dtype=np.float64)
+            self.high = np.asarray(high, dtype=np.float64)
+        else:
+            self.low = np.full(shape, low, dtype=np.float64)
+            self.high = np.full(shape, high, dtype=np.float64)
+
+    @property
+    def shape(self):
+        return self.low.shape
+
+
+class _Discrete(object):
+    def __init__(self, n):
+        self.n = n
+
+
+def _np_random(seed=None):
+    return np.random.RandomState(seed), seed
+
+
+def _module(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+_installed = False
+
+
+def install():
+    """Register the stubs and make the reference importable.  Idempotent."""
+    global _installed
+    if _installed:
+        return
+    if not reference_available():
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    if not hasattr(np, "bool"):
+        np.bool = bool  # pursuit_evade.py:476 uses the alias removed in NumPy >= 1.24
+    # rltools.util (the real file does not parse on py3.7+)
+    rl = _module("rltools")
+    rl.util = _module("rltools.util", EzPickle=_EzPickle, stack_dict_list=_stack_dict_list)
+    # gym
+    if "gym" not in sys.modules:
+        gym = _module("gym")
+        gym.spaces = _module("gym.spaces", Box=_Box, Discrete=_Discrete)
+        gym.utils = _module("gym.utils")
+        gym.utils.seeding = _module("gym.utils.seeding", np_random=_np_random)
+        gym.error = _module("gym.error", InvalidFrame=type("InvalidFrame", (Exception,), {}))
+        gym.monitoring = _module("gym.monitoring")
+        gym.monitoring.video_recorder = _module("gym.monitoring.video_recorder",
+                                                ImageEncoder=type("ImageEncoder", (object,), {}))
+    # matplotlib (render/animate only)
+    try:
+        import matplotlib.pyplot  # noqa: F401
+        import matplotlib.animation  # noqa: F401
+    except Exception:
+        mpl = _module("matplotlib")
+        mpl.animation = _module("matplotlib.animation")
+        mpl.pyplot = _module("matplotlib.pyplot")
+        mpl.patches = _module("matplotlib.patches", Rectangle=type("Rectangle", (object,), {}))
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    _installed = True
+
+
+def load_reference():
+    """Returns (MAWaterWorld, PursuitEvade, ContinuousHostageWorld) -- the real reference classes."""
+    install()
+    from madrl_environments.pursuit.waterworld import MAWaterWorld
+    from madrl_environments.pursuit.pursuit_evade import PursuitEvade
+    from madrl_environments.hostage import ContinuousHostageWorld
+    return MAWaterWorld, PursuitEvade, ContinuousHostageWorld
