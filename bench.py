@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Headline benchmark: agent-env-steps/s of the MAWaterWorld rollout hot path (BASELINE.json
+configs[1]: 5 pursuers / 5 evaders / 10 poison / 30 sensors, 4096 envs per B200).
+
+    python bench.py [--gpus N --steps K --warmup W]            # this engine
+    python bench.py --impl reference [...]                      # the CPU path on host cores
+    torchrun --nproc-per-node N bench.py --gpus N ...           # one rank per GPU, weak scaling
+
+One bench "step" = one rollout launch = T_INNER lockstep env steps of every env in the batch
+(one pass of the hot path over one batch of synthetic actions).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WW_CFG = dict(n_pursuers=5, n_evaders=5, n_poison=10, n_sensors=30)   # class defaults otherwise
+METRIC = "agent_env_steps_per_sec"
+UNIT = "agent-env-steps/s"
+
+
+def ww_bytes_per_env_step(Np, Ne, Npo, K):
+    """Algorithmic (compulsory) bytes per env-step, SURVEY.md 8(d) / BASELINE.md section 5."""
+    return 4 * (8 * (Np + Ne + Npo) + 2 * Np + Np * (7 * K + 3) + Np) + 41
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline
+def _cpu_worker(args):
+    seconds, seed = args
+    from oracle.philox import Stream
+    from oracle.waterworld_oracle import WaterworldOracle
+    env = WaterworldOracle(rng=Stream(seed, seed), **WW_CFG)
+    env.reset()
+    rs = np.random.RandomState(seed)
+    acts = rs.randn(4096, WW_CFG['n_pursuers'] * 2) * 0.5
+    for i in range(50):
+        env.step(acts[i])
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        _, _, done, _ = env.step(acts[n % 4096])
+        if done:
+            env.reset()
+        n += 1
+    return n, time.perf_counter() - t0
+
+
+def cpu_baseline(seconds, procs):
+    """The CPU path (float64 NumPy oracle port of the reference step(), one env per process the
+    way rllab's StatefulPool parallelises; rllab/rllab/sampler/stateful_pool.py:102-157)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_worker, [(seconds, 100 + i) for i in range(procs)])
+    env_steps_per_s = sum(n / dt for n, dt in res)
+    return env_steps_per_s * WW_CFG['n_pursuers']
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (weak scaling)")
+    ap.add_argument("--t-inner", type=int, default=64, help="lockstep env steps per rollout launch")
+    ap.add_argument("--cpu-seconds", type=float, default=8.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather-obs", action="store_true",
+                    help="also all-gather the full obs tensor every rollout (NVLink-bound)")
+    ap.add_argument("--wpb", type=int, default=0)
+    ap.add_argument("--bps", type=int, default=0)
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    Np = WW_CFG['n_pursuers']
+    host_cores = os.cpu_count() or 1
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        procs = host_cores
+        per = max(2.0, min(10.0, 60.0 / max(1, a.steps + a.warmup)))
+        for _ in range(a.warmup):
+            cpu_baseline(0.5, procs)
+        t0 = time.perf_counter()
+        vals = [cpu_baseline(per, procs) for _ in range(a.steps)]
+        dt = time.perf_counter() - t0
+        v = float(np.mean(vals))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "MAWaterWorld 5p/5e/10po/30 sensors, one env per host process",
+                       "envs_per_gpu": a.envs},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
+                             "sample": "%d processes x %.1f s of step() per bench step, float64 NumPy "
+                                       "oracle port of waterworld.py (the reference tree cannot travel "
+                                       "to the GPU box)" % (procs, per)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from madrl_b200 import BatchedMAWaterWorld, launch_count
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E, T = a.envs, a.t_inner
+    eng = BatchedMAWaterWorld(E, device=dev, seed=0, env_id_base=rank * E, **WW_CFG)
+    if a.wpb or a.bps:
+        eng.set_launch(a.wpb, a.bps)
+    D = eng.obs_dim
+    eng.reset()
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    # synthetic actions 0.5*N(0,1) (waterworld.py:486), a different tensor per timed step
+    n_act = min(a.steps, 4)
+    actions = [torch.randn(T, E, Np, 2, device=dev, generator=g) * 0.5 for _ in range(n_act)]
+    out = (torch.empty((T, E, Np, D), device=dev), torch.empty((T, E, Np), device=dev),
+           torch.empty((T, E), dtype=torch.uint8, device=dev),
+           torch.empty((T, E, 2), dtype=torch.int32, device=dev))
+    if world > 1:
+        g_rew = torch.empty((world,) + tuple(out[1].shape), device=dev)
+        g_done = torch.empty((world,) + tuple(out[2].shape), dtype=torch.uint8, device=dev)
+        g_info = torch.empty((world,) + tuple(out[3].shape), dtype=torch.int32, device=dev)
+        g_obs = torch.empty((world,) + tuple(out[0].shape), device=dev) if a.gather_obs else None
+
+    def one_step(i):
+        eng.rollout(actions[i % n_act], auto_reset=True, out=out)
+        if world > 1:
+            # the per-rollout gather of trajectory tensors over NVLink (rewards / dones / infos;
+            # obs stays sharded with the data-parallel learner unless --gather-obs)
+            dist.all_gather_into_tensor(g_rew, out[1])
+            dist.all_gather_into_tensor(g_done, out[2])
+            dist.all_gather_into_tensor(g_info, out[3])
+            if a.gather_obs:
+                dist.all_gather_into_tensor(g_obs, out[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, a.warmup)):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    ev0.record()
+    for i in range(a.steps):
+        kev[i][0].record()
+        eng.rollout(actions[i % n_act], auto_reset=True, out=out)
+        kev[i][1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(g_rew, out[1])
+            dist.all_gather_into_tensor(g_done, out[2])
+            dist.all_gather_into_tensor(g_info, out[3])
+            if a.gather_obs:
+                dist.all_gather_into_tensor(g_obs, out[0])
+    ev1.record()
+    barrier()
+    launches = launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    kern_ms = float(np.mean([s.elapsed_time(e) for s, e in kev]))
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    agent_steps = world * E * Np * T * a.steps
+    value = agent_steps / (ms * 1e-3)
+
+    # ---- e2e: the same rollout through the host-buffer C-ABI entry point (pinned host tensors)
+    e2e = None
+    if not a.no_e2e:
+        Te = min(T, 16)
+        h_act = [torch.randn(Te, E, Np, 2).mul_(0.5).pin_memory() for _ in range(2)]
+        h_out = (torch.empty((Te, E, Np, D)).pin_memory(), torch.empty((Te, E, Np)).pin_memory(),
+                 torch.empty((Te, E), dtype=torch.uint8).pin_memory(),
+                 torch.empty((Te, E, 2), dtype=torch.int32).pin_memory())
+        for i in range(2):
+            eng.rollout_host(h_act[i % 2], *h_out)
+        barrier()
+        n_e2e = max(3, min(a.steps, 10))
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            eng.rollout_host(h_act[i % 2], *h_out)     # returns after results are in host memory
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * E * Np * Te * n_e2e / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(h_act[0].numel() * 4),
+               "d2h_bytes_per_step": int(sum(x.numel() * x.element_size() for x in h_out)),
+               "t_inner": Te, "api": "madrl_ww_rollout_host (pinned host buffers)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    bpe = ww_bytes_per_env_step(Np, WW_CFG['n_evaders'], WW_CFG['n_poison'], WW_CFG['n_sensors'])
+    peak, peak_kind = measured_peak_gbs()
+    achieved = bpe * E * T / (kern_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": max(3, a.warmup), "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MAWaterWorld 5p/5e/10po/30 sensors, %d envs per GPU, %d lockstep "
+                               "env steps per rollout launch, auto-reset (VecEnvExecutor semantics)" % (E, T),
+                   "envs_per_gpu": E, "t_inner": T, "actions": "0.5*N(0,1), HBM-resident",
+                   "l2": "outputs per launch (%.0f MB) exceed L2" % (out[0].numel() * 4 / 1e6),
+                   "parallelism": "env-shard x%d" % world,
+                   "gather": "none" if world == 1 else ("rew/done/info" + ("+obs" if a.gather_obs else ""))},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                     "kernel": "ww_kernel<float>", "kernel_ms": kern_ms,
+                     "algorithmic_bytes_per_env_step": bpe},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary() if sampler else None,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and not a.no_cpu:
+        procs = host_cores
+        v = cpu_baseline(a.cpu_seconds, procs)
+        v1 = cpu_baseline(min(4.0, a.cpu_seconds), 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
+                                "single_core_value": v1,
+                                "sample": "%d processes x %.0f s of step() (one env each), float64 NumPy "
+                                          "oracle port of waterworld.py:220-436" % (procs, a.cpu_seconds)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,117 @@
+/* madrl_b200 -- C ABI of the B200 batched multi-agent environment engine.
+ *
+ * One handle = E independent environment instances of one family, held struct-of-arrays in
+ * HBM and stepped in lockstep by sm_100a CUDA kernels.  Every entry point replaces, for a whole
+ * batch, one method of the reference's Python environment interface
+ * (`madrl_environments/__init__.py:27-119`, AbstractMAEnv):
+ *
+ *   madrl_ww_*      <-> MAWaterWorld            madrl_environments/pursuit/waterworld.py
+ *        _reset     <-> reset()                 :144-172
+ *        _step      <-> step(action)            :220-436   (T = 1)
+ *        _rollout   <-> T x step() under rllab's VecEnvExecutor.step auto-reset contract
+ *                       rllab/sandbox/rocky/tf/envs/vec_env_executor.py:16-28
+ *        _seed      <-> seed(seed)              :135-137
+ *   madrl_pursuit_* <-> PursuitEvade            madrl_environments/pursuit/pursuit_evade.py
+ *        _reset :173-207, _step :209-262, _seed :166-168
+ *   madrl_hostage_* <-> ContinuousHostageWorld  madrl_environments/hostage.py
+ *        _reset :142-179, _step :228-429, _seed :134-136
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative MADRL_E* code and
+ *     never throws; `madrl_last_error()` returns a thread-local message for the last failure.
+ *   - `*_dev` pointers are device pointers owned by the caller (e.g. torch tensors); the
+ *     `_host` variants take host pointers and perform the host<->device copies themselves.
+ *   - the per-env state lives in one device blob.  The caller may provide it
+ *     (`state_dev`, size from `*_state_layout`) or pass NULL to let the library cudaMalloc it.
+ *     The layout (byte offsets of the struct-of-arrays fields, env index minor) is reported by
+ *     `*_state_layout` so that parity harnesses and `set_param_values`-style callers can read
+ *     and write state directly.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  One handle is used
+ *     from one host thread / stream at a time.
+ *   - randomness: counter-based Philox4x32-10 streams keyed by (seed, global env id); the
+ *     per-env draw counter is part of the state (csrc/philox.cuh).
+ *   - `real` below means float when cfg.fp64 == 0 (production) and double when cfg.fp64 == 1
+ *     (verification build used by the parity tests).
+ */
+#ifndef MADRL_B200_H
+#define MADRL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MADRL_OK 0
+#define MADRL_EINVAL (-1)   /* bad argument / unsupported configuration */
+#define MADRL_ECUDA (-2)    /* CUDA runtime error (see madrl_last_error) */
+#define MADRL_ENOMEM (-3)
+
+const char* madrl_last_error(void);
+int madrl_version(void);
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+uint64_t madrl_launch_count(void);
+
+/* ------------------------------------------------------------------ MAWaterWorld ------------ */
+typedef struct madrl_ww_config {
+  int32_t n_envs;          /* envs in THIS handle (the local shard)                              */
+  int32_t env_id_base;     /* global id of local env 0: RNG key is (seed, env_id_base + e)       */
+  int32_t n_pursuers, n_evaders, n_poison, n_sensors, n_coop;   /* waterworld.py:77-79          */
+  int32_t reward_global;   /* reward_mech == 'global'                                            */
+  int32_t addid, speed_features;
+  int32_t random_obstacle; /* obstacle_loc is None -> drawn at reset (waterworld.py:147-148)     */
+  int32_t timestep_limit;  /* 1000 (waterworld.py:124-126)                                       */
+  int32_t max_path_length; /* VecEnvExecutor horizon, 0 = none                                   */
+  int32_t fp64;            /* 0: fp32 arithmetic and buffers; 1: fp64 verification build         */
+  double radius, obstacle_radius, obstacle_x, obstacle_y, ev_speed, poison_speed, sensor_range,
+      action_scale, poison_reward, food_reward, encounter_reward, control_penalty;
+  uint64_t seed;
+} madrl_ww_config;
+
+/* Byte offsets into the state blob.  Arrays are [object][n_envs] (env minor); objects are
+ * ordered pursuers, evaders, poisons. */
+typedef struct madrl_ww_layout {
+  size_t total_bytes;
+  size_t pos_x, pos_y, vel_x, vel_y;   /* real [n_obj][E]                                      */
+  size_t obst_x, obst_y;               /* real [E]                                             */
+  size_t timestep;                     /* int32 [E]  env._timesteps                            */
+  size_t path_len;                     /* int32 [E]  VecEnvExecutor.ts                         */
+  size_t rng_counter;                  /* uint64 [E] draws consumed                            */
+  size_t sensors;                      /* real [2][n_sensors] unit vectors (cos row, sin row)  */
+  int32_t n_obj, obs_dim, real_bytes, _pad;
+} madrl_ww_layout;
+
+typedef struct madrl_ww madrl_ww;
+
+int madrl_ww_state_layout(const madrl_ww_config* cfg, madrl_ww_layout* out);
+int madrl_ww_create(const madrl_ww_config* cfg, void* state_dev, madrl_ww** out);
+int madrl_ww_destroy(madrl_ww* h);
+void* madrl_ww_state_ptr(madrl_ww* h);
+/* seed(): new key, draw counters reset to 0 (waterworld.py:135-137 creates a fresh generator). */
+int madrl_ww_seed(madrl_ww* h, uint64_t seed, void* stream);
+/* Launch geometry override (0 = library default): warps per block, blocks per SM. */
+int madrl_ww_set_launch(madrl_ww* h, int warps_per_block, int blocks_per_sm);
+
+/* reset(): envs with mask_dev[e] != 0 (all if NULL) are re-initialised and advanced by the
+ * reference's internal step(zeros); obs_dev real [E][Np][obs_dim], rows of unmasked envs untouched. */
+int madrl_ww_reset(madrl_ww* h, const uint8_t* mask_dev, void* obs_dev, void* stream);
+/* T lockstep steps in ONE launch.  actions_dev real [T][E][Np][2]; obs_dev real [T][E][Np][obs_dim];
+ * rew_dev real [T][E][Np]; done_dev uint8 [T][E]; info_dev int32 [T][E][2] = (evcatches, pocatches).
+ * auto_reset != 0: VecEnvExecutor.step semantics -- a done env is reset in place and the obs
+ * slot of that step holds the reset observation. */
+int madrl_ww_rollout(madrl_ww* h, int T, const void* actions_dev, void* obs_dev, void* rew_dev,
+                     uint8_t* done_dev, int32_t* info_dev, int auto_reset, void* stream);
+/* step() == rollout with T = 1. */
+int madrl_ww_step(madrl_ww* h, const void* actions_dev, void* obs_dev, void* rew_dev,
+                  uint8_t* done_dev, int32_t* info_dev, int auto_reset, void* stream);
+/* Host-buffer variants (what a non-torch FFI caller binds): copies are part of the call and the
+ * call returns after the results are in the host buffers. */
+int madrl_ww_reset_host(madrl_ww* h, const uint8_t* mask_host, void* obs_host);
+int madrl_ww_rollout_host(madrl_ww* h, int T, const void* actions_host, void* obs_host,
+                          void* rew_host, uint8_t* done_host, int32_t* info_host, int auto_reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MADRL_B200_H */

@@ -1,0 +1,87 @@
+"""ctypes binding of the C ABI declared in ``include/madrl_b200.h``.
+
+The CUDA library is the product: if it cannot be loaded there is NO fallback -- importing an
+engine class raises.  PyTorch is used only to own device memory and streams.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class WWConfig(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32), ("env_id_base", C.c_int32),
+        ("n_pursuers", C.c_int32), ("n_evaders", C.c_int32), ("n_poison", C.c_int32),
+        ("n_sensors", C.c_int32), ("n_coop", C.c_int32),
+        ("reward_global", C.c_int32), ("addid", C.c_int32), ("speed_features", C.c_int32),
+        ("random_obstacle", C.c_int32), ("timestep_limit", C.c_int32),
+        ("max_path_length", C.c_int32), ("fp64", C.c_int32),
+        ("radius", C.c_double), ("obstacle_radius", C.c_double), ("obstacle_x", C.c_double),
+        ("obstacle_y", C.c_double), ("ev_speed", C.c_double), ("poison_speed", C.c_double),
+        ("sensor_range", C.c_double), ("action_scale", C.c_double), ("poison_reward", C.c_double),
+        ("food_reward", C.c_double), ("encounter_reward", C.c_double),
+        ("control_penalty", C.c_double), ("seed", C.c_uint64),
+    ]
+
+
+class WWLayout(C.Structure):
+    _fields_ = [
+        ("total_bytes", C.c_size_t),
+        ("pos_x", C.c_size_t), ("pos_y", C.c_size_t), ("vel_x", C.c_size_t), ("vel_y", C.c_size_t),
+        ("obst_x", C.c_size_t), ("obst_y", C.c_size_t), ("timestep", C.c_size_t),
+        ("path_len", C.c_size_t), ("rng_counter", C.c_size_t), ("sensors", C.c_size_t),
+        ("n_obj", C.c_int32), ("obs_dim", C.c_int32), ("real_bytes", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
+def _declare(lib):
+    vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
+    lib.madrl_last_error.restype = C.c_char_p
+    lib.madrl_version.restype = C.c_int
+    lib.madrl_launch_count.restype = C.c_uint64
+    lib.madrl_ww_state_layout.argtypes = [C.POINTER(WWConfig), C.POINTER(WWLayout)]
+    lib.madrl_ww_create.argtypes = [C.POINTER(WWConfig), vp, C.POINTER(vp)]
+    lib.madrl_ww_destroy.argtypes = [vp]
+    lib.madrl_ww_state_ptr.argtypes = [vp]
+    lib.madrl_ww_state_ptr.restype = vp
+    lib.madrl_ww_seed.argtypes = [vp, u64, vp]
+    lib.madrl_ww_set_launch.argtypes = [vp, i32, i32]
+    lib.madrl_ww_reset.argtypes = [vp, vp, vp, vp]
+    lib.madrl_ww_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp]
+    lib.madrl_ww_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
+    lib.madrl_ww_reset_host.argtypes = [vp, vp, vp]
+    lib.madrl_ww_rollout_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
+
+
+def lib():
+    """Load (building if needed) the CUDA library.  Raises EngineError on failure."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB
+        if not os.path.exists(path) or os.environ.get("MADRL_B200_REBUILD"):
+            try:
+                path = _build.build()
+            except Exception as e:  # no nvcc / compile error: there is no CPU fallback
+                raise EngineError("madrl_b200 CUDA library is missing and could not be built: %s" % e)
+        try:
+            _lib = C.CDLL(path)
+        except OSError as e:
+            raise EngineError("cannot load %s: %s" % (path, e))
+        _declare(_lib)
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise EngineError("madrl_b200 error %d: %s" % (rc, lib().madrl_last_error().decode()))
+
+
+def launch_count():
+    return int(lib().madrl_launch_count())
