@@ -69,12 +69,13 @@ typedef struct madrl_ww_config {
   uint64_t seed;
 } madrl_ww_config;
 
-/* Byte offsets into the state blob.  Arrays are [object][n_envs] (env minor); objects are
- * ordered pursuers, evaders, poisons. */
+/* Byte offsets into the state blob.  The dynamic state is one record per env:
+ * objs real [E][4][n_obj] = rows x, y, vx, vy; objects ordered pursuers, evaders, poisons
+ * (one warp owns one env, so a record is one coalesced read per launch). */
 typedef struct madrl_ww_layout {
   size_t total_bytes;
-  size_t pos_x, pos_y, vel_x, vel_y;   /* real [n_obj][E]                                      */
-  size_t obst_x, obst_y;               /* real [E]                                             */
+  size_t objs;                         /* real [E][4][n_obj]                                   */
+  size_t obst;                         /* real [E][2] obstacle centre                          */
   size_t timestep;                     /* int32 [E]  env._timesteps                            */
   size_t path_len;                     /* int32 [E]  VecEnvExecutor.ts                         */
   size_t rng_counter;                  /* uint64 [E] draws consumed                            */
@@ -90,7 +91,7 @@ int madrl_ww_destroy(madrl_ww* h);
 void* madrl_ww_state_ptr(madrl_ww* h);
 /* seed(): new key, draw counters reset to 0 (waterworld.py:135-137 creates a fresh generator). */
 int madrl_ww_seed(madrl_ww* h, uint64_t seed, void* stream);
-/* Launch geometry override (0 = library default): warps per block, blocks per SM. */
+/* Launch geometry override (0 = library default): warps (= envs) per block <= 4, blocks per SM. */
 int madrl_ww_set_launch(madrl_ww* h, int warps_per_block, int blocks_per_sm);
 
 /* reset(): envs with mask_dev[e] != 0 (all if NULL) are re-initialised and advanced by the

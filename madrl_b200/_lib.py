@@ -33,10 +33,9 @@ class WWConfig(C.Structure):
 
 class WWLayout(C.Structure):
     _fields_ = [
-        ("total_bytes", C.c_size_t),
-        ("pos_x", C.c_size_t), ("pos_y", C.c_size_t), ("vel_x", C.c_size_t), ("vel_y", C.c_size_t),
-        ("obst_x", C.c_size_t), ("obst_y", C.c_size_t), ("timestep", C.c_size_t),
-        ("path_len", C.c_size_t), ("rng_counter", C.c_size_t), ("sensors", C.c_size_t),
+        ("total_bytes", C.c_size_t), ("objs", C.c_size_t), ("obst", C.c_size_t),
+        ("timestep", C.c_size_t), ("path_len", C.c_size_t), ("rng_counter", C.c_size_t),
+        ("sensors", C.c_size_t),
         ("n_obj", C.c_int32), ("obs_dim", C.c_int32), ("real_bytes", C.c_int32), ("_pad", C.c_int32),
     ]
 

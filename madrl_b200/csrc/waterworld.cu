@@ -1,25 +1,26 @@
-// MAWaterWorld batched engine: persistent multi-step rollout kernel for sm_100a.
+// MAWaterWorld batched engine: persistent warp-per-env rollout kernel for sm_100a.
 //
 // Reference semantics: madrl_environments/pursuit/waterworld.py (cited as ww:LINE).
 //
 // Design:
-//   * HBM state is struct-of-arrays, env index minor: pos/vel [object][E], so a block's
-//     contiguous env range loads/stores short coalesced runs; trajectory tensors are
-//     [T][E][Np][D] (agent rows contiguous -- the layout the reference callers consume).
-//   * A block owns a contiguous range of envs for the WHOLE T-step rollout.  Their state is
-//     staged into shared memory once and never touches HBM again until the rollout ends;
-//     per step the only HBM traffic is actions in and obs / reward / done / info out.
-//   * Per step, two block phases:
-//       "env phase"  one warp per env, lanes over objects: integrate + walls + obstacle
-//                    rebound (ww:229-270) for step t, fused with the tail of step t-1
-//                    (catch bookkeeping, respawn, rewards, evader drift, ww:358-409,433-436);
-//       "sense phase" one warp per (env, pursuer), lanes over objects then over sensors:
-//                    pairwise collisions via __ballot_sync (ww:278-293), exact conservative
-//                    range cull via ballot, nearest-object-per-sensor over the surviving
-//                    candidates (ww:64-72,312-353), coalesced feature-major obs row stores
-//                    (ww:388-428).
+//   * One WARP owns one env for the WHOLE T-step rollout.  The env's state lives in REGISTERS:
+//     lane l holds objects l, l+32, ... (position + velocity); objects are ordered pursuers,
+//     evaders, poisons.  There is no shared memory and no block barrier anywhere: warps are
+//     completely independent, so the SM's schedulers overlap the phases of different envs.
+//     HBM sees the state once per launch (a coalesced per-env record) and, per step, only
+//     actions in and obs / reward / done / info out.
+//   * Per step and pursuer, lanes act first as OBJECTS (relative position, squared distance,
+//     collision test and exact conservative range cull, all reduced with __ballot_sync), then as
+//     SENSORS (lane k = sensor k) looping over the few surviving candidates, whose geometry is
+//     broadcast with __shfl_sync; nearest-object-per-sensor keeps the lowest index among equal
+//     minima (np.argmin).  The 7 feature rows of the pursuer are stored as coalesced
+//     feature-major runs straight from registers.
+//   * sqrt-free thresholds: every `cdist(...) <= thr` of the reference is evaluated as
+//     d2 <= thr2 with thr2 the largest representable value whose correctly-rounded sqrt is
+//     <= thr (computed on the host), which is exactly equivalent.
 //   * fp32 production instantiation and fp64 verification instantiation of the same template.
 #include <math.h>
+#include <cmath>
 #include <new>
 
 #include "common.cuh"
@@ -29,22 +30,22 @@ namespace madrl {
 
 template <typename real>
 struct WWParams {
-  int E, env_id_base, Np, Ne, Npo, K, n_coop, D, Nall, CW;
+  int E, env_id_base, Np, Ne, Npo, K, n_coop, D, Nall;
   int reward_global, addid, speed_features, random_obstacle, timestep_limit, max_path_length;
   int T, mode, auto_reset;  // mode 0 = rollout, 1 = reset
-  int max_loc, env_stride;  // envs per block (max), bytes per env slot in smem
-  int off_py, off_vx, off_vy, off_rew, off_coll, off_meta, off_ctr;  // byte offsets in a slot
-  real r_p2, range, cull2, rsum_e, rsum_po;          // sensing / collision thresholds
-  real thr_obst_p, thr_obst_e, thr_obst_po;          // r_class + obstacle_radius (ww:251,259,267)
-  real thr_resp_p, thr_resp_e, thr_resp_po;          // 2 r_class + obstacle_radius (ww:140)
+  real r_p2, range, cull2;                           // sensing thresholds (ww:68-69)
+  real coll2_e, coll2_po;                            // (r_p + r_obj) as exact squared thresholds
+  real obst2_p, obst2_e, obst2_po;                   // (r_class + R_obst)       ww:251,259,267
+  real resp2_p, resp2_e, resp2_po;                   // (2 r_class + R_obst)     ww:140
   real obst_x, obst_y, ev_speed, poison_speed, action_scale;
   real poison_reward, food_reward, encounter_reward, control_penalty;
   uint64_t seed;
-  // state (SoA, env minor)
-  real *pos_x, *pos_y, *vel_x, *vel_y, *obst_px, *obst_py;
+  // state: per-env records
+  real* objs;         // [E][4][Nall]  (x, y, vx, vy rows)
+  real* obst;         // [E][2]
   int32_t *timestep, *path_len;
   uint64_t* ctr;
-  const real* sensors;
+  const real* sensors;  // [2][K]
   // trajectory tensors
   const real* actions;
   real* obs;
@@ -59,395 +60,321 @@ template <> struct Vec2<float> { typedef float2 type; };
 template <> struct Vec2<double> { typedef double2 type; };
 
 template <typename real>
-struct EnvSlot {
-  real *px, *py, *vx, *vy, *rew;
-  uint32_t* coll;  // [Np][CW] bit o set <=> pursuer row collides with evader/poison object o
-  int32_t* meta;   // 0: timestep, 1: path_len, 2: needs_reset
-  uint64_t* ctr;
-};
-
-template <typename real>
-__device__ __forceinline__ EnvSlot<real> env_slot(const WWParams<real>& p, char* base, int slot) {
-  char* b = base + (size_t)slot * p.env_stride;
-  EnvSlot<real> s;
-  s.px = reinterpret_cast<real*>(b);
-  s.py = reinterpret_cast<real*>(b + p.off_py);
-  s.vx = reinterpret_cast<real*>(b + p.off_vx);
-  s.vy = reinterpret_cast<real*>(b + p.off_vy);
-  s.rew = reinterpret_cast<real*>(b + p.off_rew);
-  s.coll = reinterpret_cast<uint32_t*>(b + p.off_coll);
-  s.meta = reinterpret_cast<int32_t*>(b + p.off_meta);
-  s.ctr = reinterpret_cast<uint64_t*>(b + p.off_ctr);
-  return s;
-}
-
-template <typename real>
 __device__ __forceinline__ real warp_sum(real v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
   return v;
 }
 
-// ww:139-142  rejection loop around the obstacle (lane-serial, rare).
 template <typename real>
-__device__ __forceinline__ void spawn_point(SeqStream& rs, real obx, real oby, real thr, real& x,
-                                            real& y) {
-  x = rs.next_unit<real>();
-  y = rs.next_unit<real>();
-  while (true) {
-    const real dx = x - obx, dy = y - oby;
-    if (!(sqrt(dx * dx + dy * dy) <= thr)) break;
-    x = rs.next_unit<real>();
-    y = rs.next_unit<real>();
-  }
-}
+struct Spawn { real x, y, vx, vy; uint64_t ctr; };
 
-// ww:144-170  reset draws, in the reference's order (obstacle, pursuers, evaders, poisons).
+// ww:139-142 + ww:360-374: rejection-sample a position outside the obstacle's keep-out disc,
+// then (optionally) a velocity.  Executed warp-uniformly (every lane runs the same stream), so
+// no broadcast is needed; rare, hence not inlined into the hot loop.
 template <typename real>
-__device__ void env_reset_draws(const WWParams<real>& p, const EnvSlot<real>& s, int e, int lane) {
-  if (lane == 0) {
-    SeqStream rs;
-    rs.init(p.seed, (uint32_t)(p.env_id_base + e), 0u, *s.ctr);
-    real obx = p.obst_x, oby = p.obst_y;
-    if (p.random_obstacle) {
-      obx = rs.next_unit<real>();
-      oby = rs.next_unit<real>();
-    }
-    s.px[p.Nall] = obx;
-    s.py[p.Nall] = oby;
-    for (int o = 0; o < p.Nall; ++o) {
-      const bool isP = o < p.Np, isE = !isP && o < p.Np + p.Ne;
-      real x, y;
-      spawn_point<real>(rs, obx, oby, isP ? p.thr_resp_p : (isE ? p.thr_resp_e : p.thr_resp_po), x, y);
-      real vx = 0, vy = 0;
-      if (!isP) {  // ww:164,170 -- poisons also use ev_speed at reset
-        vx = (rs.next_unit<real>() - (real)0.5) * p.ev_speed;
-        vy = (rs.next_unit<real>() - (real)0.5) * p.ev_speed;
-      }
-      s.px[o] = x; s.py[o] = y; s.vx[o] = vx; s.vy[o] = vy;
-    }
-    *s.ctr = rs.counter;
-    s.meta[0] = 0;
-    s.meta[1] = 0;
-  }
-  __syncwarp();
-}
-
-// ww:221-270  integrate pursuers, control penalty, walls, obstacle rebound (all objects).
-template <typename real>
-__device__ void env_pre(const WWParams<real>& p, const EnvSlot<real>& s, int e, int t,
-                        bool zero_action, int lane) {
-  const real obx = s.px[p.Nall], oby = s.py[p.Nall];
-  real sq_tot = 0;
-  for (int base = 0; base < p.Nall; base += 32) {
-    const int o = base + lane;
-    real sq = 0;
-    if (o < p.Nall) {
-      real x = s.px[o], y = s.py[o], vx = s.vx[o], vy = s.vy[o];
-      real thr, k;
-      if (o < p.Np) {
-        real ax = 0, ay = 0;
-        if (!zero_action) {
-          typedef typename Vec2<real>::type V2;
-          const V2 a = reinterpret_cast<const V2*>(p.actions)[((size_t)t * p.E + e) * p.Np + o];
-          ax = a.x * p.action_scale;
-          ay = a.y * p.action_scale;
-        }
-        vx += ax; vy += ay;
-        x += vx;  y += vy;
-        sq = ax * ax + ay * ay;
-        const real cx = clip01(x), cy = clip01(y);
-        if (x != cx) vx = 0;
-        if (y != cy) vy = 0;
-        x = cx; y = cy;
-        thr = p.thr_obst_p; k = (real)-0.5;
-        if (!p.reward_global) s.rew[o] = p.control_penalty * sq;
-      } else if (o < p.Np + p.Ne) {
-        thr = p.thr_obst_e; k = (real)-0.5;
-      } else {
-        thr = p.thr_obst_po; k = (real)-1;
-      }
-      const real dx = x - obx, dy = y - oby;
-      if (sqrt(dx * dx + dy * dy) <= thr) { vx = k * vx; vy = k * vy; }
-      s.px[o] = x; s.py[o] = y; s.vx[o] = vx; s.vy[o] = vy;
-    }
-    if (p.reward_global && base < p.Np) sq_tot += warp_sum(sq);
-  }
-  if (p.reward_global) {
-    for (int o = lane; o < p.Np; o += 32) s.rew[o] = p.control_penalty * sq_tot;
-  }
-}
-
-// ww:285,293,358-385,397-409,433-436  catches, respawn, rewards, drift, bookkeeping.
-template <typename real>
-__device__ void env_post(const WWParams<real>& p, const EnvSlot<real>& s, int e, int t,
-                         bool discard, int lane) {
+__device__ __noinline__ Spawn<real> spawn_object(uint64_t seed, uint32_t env_id, uint64_t ctr,
+                                                 real obx, real oby, real thr2, real speed,
+                                                 int with_velocity) {
   SeqStream rs;
-  rs.init(p.seed, (uint32_t)(p.env_id_base + e), 0u, *s.ctr);
-  const real obx = s.px[p.Nall], oby = s.py[p.Nall];
-  unsigned whoE = 0, whoP = 0, whoEnc = 0;
-  int nE = 0, nP = 0, nEnc = 0;
-  for (int base = p.Np; base < p.Nall; base += 32) {
-    const int o = base + lane;
-    const bool v = o < p.Nall;
-    unsigned col = 0;
-    if (v) {
-      for (int q = 0; q < p.Np; ++q) col |= ((s.coll[q * p.CW + (o >> 5)] >> (o & 31)) & 1u) << q;
-    }
-    const int cnt = __popc(col);
-    const bool isE = o < p.Np + p.Ne;
-    const bool caught = v && (isE ? cnt >= p.n_coop : cnt >= 1);   // ww:285 / ww:293
-    const bool enc = v && isE && cnt >= 1;                          // ww:376
-    const unsigned cm = __ballot_sync(FULL_MASK, caught);
-    const unsigned cmE = __ballot_sync(FULL_MASK, caught && isE);
-    nE += __popc(cmE);
-    nP += __popc(cm & ~cmE);
-    nEnc += __popc(__ballot_sync(FULL_MASK, enc));
-    if (caught) { if (isE) whoE |= col; else whoP |= col; }
-    if (enc) whoEnc |= col;
-    if (cm != 0u) {
-      if (lane == 0) {  // ww:358-374, ascending object index = evaders first, then poisons
-        unsigned m = cm;
-        while (m) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1;
-          const int oj = base + j;
-          const bool jE = oj < p.Np + p.Ne;
-          real x, y;
-          spawn_point<real>(rs, obx, oby, jE ? p.thr_resp_e : p.thr_resp_po, x, y);
-          const real sp = jE ? p.ev_speed : p.poison_speed;
-          s.px[oj] = x; s.py[oj] = y;
-          s.vx[oj] = (rs.next_unit<real>() - (real)0.5) * sp;
-          s.vy[oj] = (rs.next_unit<real>() - (real)0.5) * sp;
-        }
-      }
-      __syncwarp();
-    }
+  rs.init(seed, env_id, 0u, ctr);
+  Spawn<real> s;
+  s.x = rs.next_unit<real>();
+  s.y = rs.next_unit<real>();
+  while (true) {
+    const real dx = s.x - obx, dy = s.y - oby;
+    if (!(dx * dx + dy * dy <= thr2)) break;
+    s.x = rs.next_unit<real>();
+    s.y = rs.next_unit<real>();
   }
-  whoE = __reduce_or_sync(FULL_MASK, whoE);
-  whoP = __reduce_or_sync(FULL_MASK, whoP);
-  whoEnc = __reduce_or_sync(FULL_MASK, whoEnc);
-  // rewards ww:376-385
-  if (!discard) {
-    for (int q = lane; q < p.Np; q += 32) {
-      real r = s.rew[q];
-      if (p.reward_global) {
-        r += ((real)nE * p.food_reward + (real)nP * p.poison_reward) + (real)nEnc * p.encounter_reward;
-      } else {
-        if ((whoE >> q) & 1u) r += p.food_reward;
-        if ((whoP >> q) & 1u) r += p.poison_reward;
-        if ((whoEnc >> q) & 1u) r += p.encounter_reward;
-      }
-      store_stream(p.rew + ((size_t)t * p.E + e) * p.Np + q, r);
-    }
+  s.vx = 0; s.vy = 0;
+  if (with_velocity) {
+    s.vx = (rs.next_unit<real>() - (real)0.5) * speed;
+    s.vy = (rs.next_unit<real>() - (real)0.5) * speed;
   }
-  // evaders / poison drift, ww:397-409
-  for (int o = p.Np + lane; o < p.Nall; o += 32) {
-    real x = s.px[o] + s.vx[o], y = s.py[o] + s.vy[o];
-    s.px[o] = x; s.py[o] = y;
-    const bool ox = (x < (real)0) || (x > (real)1), oy = (y < (real)0) || (y > (real)1);
-    if (ox && oy) { s.vx[o] = -s.vx[o]; s.vy[o] = -s.vy[o]; }
-  }
-  if (lane == 0) {
-    *s.ctr = rs.counter;
-    const int tt = s.meta[0] + 1, ts = s.meta[1] + 1;  // ww:433
-    s.meta[0] = tt;
-    s.meta[1] = ts;
-    const bool done = (tt >= p.timestep_limit) || (p.max_path_length > 0 && ts >= p.max_path_length);
-    if (!discard) {
-      p.done[(size_t)t * p.E + e] = done ? 1 : 0;
-      p.info[((size_t)t * p.E + e) * 2 + 0] = nE;
-      p.info[((size_t)t * p.E + e) * 2 + 1] = nP;
-      s.meta[2] = (done && p.auto_reset) ? 1 : 0;
-    } else {
-      s.meta[2] = 0;
-    }
-  }
-  __syncwarp();
+  s.ctr = rs.counter;
+  return s;
 }
 
-// ww:64-72,278-353,388-428  one (env, pursuer): collisions, sensing, obs row.
-template <typename real>
-__device__ void sense_item(const WWParams<real>& p, const EnvSlot<real>& s, const real* sens,
-                           int pi, int lane, real* __restrict__ obs_row) {
+template <typename real, int OPL, int KCH>
+__global__ void __launch_bounds__(128, (OPL <= 2 ? 7 : 4))
+ww_kernel(const __grid_constant__ WWParams<real> p) {
   const real INF = real_inf<real>();
-  const real mx = s.px[pi], my = s.py[pi], mvx = s.vx[pi], mvy = s.vy[pi];
-  const int Nobj = p.Nall + 1;  // obstacle is object index Nall
-  const int eLo = p.Np, eHi = p.Np + p.Ne;
-  bool anyE = false, anyP = false;
-  for (int ks = 0; ks < p.K; ks += 32) {
-    const int k = ks + lane;
-    const bool kval = k < p.K;
-    const real sx = kval ? sens[k] : (real)0, sy = kval ? sens[p.K + k] : (real)0;
-    real bU = INF, bE = INF, bP = INF, bO = INF;
-    int iU = 0, iE = 0, iP = 0;
-    for (int base = 0; base < Nobj; base += 32) {
-      const int o = base + lane;
-      const bool valid = o < Nobj;
-      real d2 = INF;
-      if (valid) {
-        const real rx = s.px[o] - mx, ry = s.py[o] - my;
-        d2 = rx * rx + ry * ry;
-      }
-      unsigned cm = __ballot_sync(FULL_MASK, valid && (d2 <= p.cull2) && (o != pi));
-      if (ks == 0) {  // pairwise collisions, ww:278-293
-        const bool isE = o >= eLo && o < eHi, isP = o >= eHi && o < p.Nall;
-        const real dist = sqrt(d2);
-        const bool c = (isE && dist <= p.rsum_e) || (isP && dist <= p.rsum_po);
-        const unsigned m = __ballot_sync(FULL_MASK, c);
-        anyE |= __ballot_sync(FULL_MASK, c && isE) != 0u;
-        anyP |= __ballot_sync(FULL_MASK, c && isP) != 0u;
-        if (lane == 0) s.coll[pi * p.CW + (base >> 5)] = m;
-      }
-      while (cm) {  // warp-uniform loop over in-range candidates, ascending index
-        const int j = __ffs(cm) - 1;
-        cm &= cm - 1;
-        const int oj = base + j;
-        const real rx = s.px[oj] - mx, ry = s.py[oj] - my;
-        const real q2 = rx * rx + ry * ry;
-        const real sv = sx * rx + sy * ry;                                 // ww:67
-        const bool ok = !((sv < (real)0) | (sv > p.range) | (q2 - sv * sv > p.r_p2));  // ww:68-69
-        if (oj < eLo)        { if (ok && sv < bU) { bU = sv; iU = oj; } }
-        else if (oj < eHi)   { if (ok && sv < bE) { bE = sv; iE = oj; } }
-        else if (oj < p.Nall){ if (ok && sv < bP) { bP = sv; iP = oj; } }
-        else                 { if (ok && sv < bO) { bO = sv; } }
-      }
-    }
-    if (kval) {  // ww:312-353, 388-395: feature-major, sensor-minor
-      const bool hO = bO < INF, hE = bE < INF, hP = bP < INF, hU = bU < INF;
-      const real z = (real)0;
-      if (p.speed_features) {
-        const real sE = hE ? sx * (s.vx[iE] - mvx) + sy * (s.vy[iE] - mvy) : z;
-        const real sP = hP ? sx * (s.vx[iP] - mvx) + sy * (s.vy[iP] - mvy) : z;
-        const real sU = hU ? sx * (s.vx[iU] - mvx) + sy * (s.vy[iU] - mvy) : z;
-        store_stream(obs_row + 0 * p.K + k, hO ? bO : z);
-        store_stream(obs_row + 1 * p.K + k, hE ? bE : z);
-        store_stream(obs_row + 2 * p.K + k, sE);
-        store_stream(obs_row + 3 * p.K + k, hP ? bP : z);
-        store_stream(obs_row + 4 * p.K + k, sP);
-        store_stream(obs_row + 5 * p.K + k, hU ? bU : z);
-        store_stream(obs_row + 6 * p.K + k, sU);
-      } else {
-        store_stream(obs_row + 0 * p.K + k, hO ? bO : z);
-        store_stream(obs_row + 1 * p.K + k, hE ? bE : z);
-        store_stream(obs_row + 2 * p.K + k, hP ? bP : z);
-        store_stream(obs_row + 3 * p.K + k, hU ? bU : z);
-      }
-    }
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int warp_stride = gridDim.x * warps_per_block;
+  const int eLo = p.Np, eHi = p.Np + p.Ne, Nall = p.Nall;
+
+  // ---- per-lane constants: this lane as OBJECT (classes, thresholds) and as SENSOR -----------
+  real cull2_l[OPL], coll2_l[OPL], obst2_l[OPL], kf_l[OPL];
+  int need_l[OPL];               // collisions needed to be caught (ww:285: n_coop, ww:293: 1)
+  unsigned mE[OPL], mP[OPL], mU[OPL];  // warp-uniform class masks of each object chunk
+#pragma unroll
+  for (int c = 0; c < OPL; ++c) {
+    const int o = lane + 32 * c;
+    const bool isU = o < eLo, isE = o >= eLo && o < eHi, isP = o >= eHi && o < Nall;
+    cull2_l[c] = (o < Nall) ? p.cull2 : (real)-1;
+    coll2_l[c] = isE ? p.coll2_e : (isP ? p.coll2_po : (real)-1);
+    obst2_l[c] = isU ? p.obst2_p : (isE ? p.obst2_e : (isP ? p.obst2_po : (real)-1));
+    kf_l[c] = isP ? (real)-1 : (real)-0.5;                      // ww:254,262,270
+    need_l[c] = isE ? p.n_coop : (isP ? 1 : 0x7fffffff);
+    mU[c] = __ballot_sync(FULL_MASK, isU);
+    mE[c] = __ballot_sync(FULL_MASK, isE);
+    mP[c] = __ballot_sync(FULL_MASK, isP);
   }
-  // ww:411-428 tail: collided-with-evader, collided-with-poison, id
-  const int tail = p.K * (p.speed_features ? 7 : 4);
-  if (lane == 0) store_stream(obs_row + tail, anyE ? (real)1 : (real)0);
-  if (lane == 1) store_stream(obs_row + tail + 1, anyP ? (real)1 : (real)0);
-  if (lane == 2 && p.addid) store_stream(obs_row + tail + 2, (real)(pi + 1));
-}
-
-template <typename real>
-__global__ void __launch_bounds__(512) ww_kernel(const __grid_constant__ WWParams<real> p) {
-  extern __shared__ __align__(16) char smem[];
-  real* sens = reinterpret_cast<real*>(smem);
-  char* slots = smem + (((size_t)2 * p.K * sizeof(real) + 15) / 16) * 16;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
-  const int e0 = (int)(((long long)blockIdx.x * p.E) / gridDim.x);
-  const int e1 = (int)(((long long)(blockIdx.x + 1) * p.E) / gridDim.x);
-  const int n_loc = e1 - e0;
-  if (n_loc <= 0) return;
-
-  // ---- stage state: HBM (SoA, env minor) -> shared memory --------------------------------
-  for (int i = tid; i < 2 * p.K; i += blockDim.x) sens[i] = p.sensors[i];
-  for (int i = tid; i < n_loc * p.Nall; i += blockDim.x) {
-    const int el = i % n_loc, o = i / n_loc;
-    const EnvSlot<real> s = env_slot(p, slots, el);
-    const size_t g = (size_t)o * p.E + e0 + el;
-    s.px[o] = p.pos_x[g]; s.py[o] = p.pos_y[g]; s.vx[o] = p.vel_x[g]; s.vy[o] = p.vel_y[g];
+  real sx_l[KCH], sy_l[KCH];
+#pragma unroll
+  for (int kc = 0; kc < KCH; ++kc) {
+    const int k = lane + 32 * kc;
+    sx_l[kc] = (k < p.K) ? p.sensors[k] : (real)0;
+    sy_l[kc] = (k < p.K) ? p.sensors[p.K + k] : (real)0;
   }
-  for (int el = tid; el < n_loc; el += blockDim.x) {
-    const EnvSlot<real> s = env_slot(p, slots, el);
-    s.px[p.Nall] = p.obst_px[e0 + el];
-    s.py[p.Nall] = p.obst_py[e0 + el];
-    s.meta[0] = p.timestep[e0 + el];
-    s.meta[1] = p.path_len[e0 + el];
-    s.meta[2] = (p.mode == 1) ? ((p.mask == nullptr || p.mask[e0 + el]) ? 1 : 0) : 0;
-    *s.ctr = p.ctr[e0 + el];
-  }
-  __syncthreads();
+  const int n_feat = p.speed_features ? 7 : 4;
+  typedef typename Vec2<real>::type V2;
 
-  const int n_items = n_loc * p.Np;
-  if (p.mode == 1) {
-    // ---- reset(): draws + the reference's internal step(zeros), obs only (ww:144-172) ------
-    for (int el = warp; el < n_loc; el += NW) {
-      const EnvSlot<real> s = env_slot(p, slots, el);
-      if (s.meta[2]) { env_reset_draws(p, s, e0 + el, lane); env_pre(p, s, e0 + el, 0, true, lane); }
+  for (int e = warp_global; e < p.E; e += warp_stride) {
+    if (p.mode == 1 && p.mask != nullptr && p.mask[e] == 0) continue;
+    const uint32_t env_id = (uint32_t)(p.env_id_base + e);
+    // ---- state: HBM record -> registers -----------------------------------------------------
+    real x[OPL], y[OPL], vx[OPL], vy[OPL];
+    unsigned col[OPL];  // per object: bit q set <=> pursuer q collides with it this step
+    real* rec = p.objs + (size_t)e * 4 * Nall;
+#pragma unroll
+    for (int c = 0; c < OPL; ++c) {
+      const int o = lane + 32 * c;
+      const bool v = o < Nall;
+      x[c] = v ? rec[o] : (real)0;
+      y[c] = v ? rec[Nall + o] : (real)0;
+      vx[c] = v ? rec[2 * Nall + o] : (real)0;
+      vy[c] = v ? rec[3 * Nall + o] : (real)0;
+      col[c] = 0u;
     }
-    __syncthreads();
-    for (int it = warp; it < n_items; it += NW) {
-      const int el = it / p.Np, pi = it - el * p.Np;
-      const EnvSlot<real> s = env_slot(p, slots, el);
-      if (s.meta[2]) sense_item(p, s, sens, pi, lane, p.obs + ((size_t)(e0 + el) * p.Np + pi) * p.D);
-    }
-    __syncthreads();
-    for (int el = warp; el < n_loc; el += NW) {
-      const EnvSlot<real> s = env_slot(p, slots, el);
-      if (s.meta[2]) env_post(p, s, e0 + el, 0, true, lane);
-    }
-  } else {
+    real obx = p.obst[2 * (size_t)e], oby = p.obst[2 * (size_t)e + 1];
+    int tt = p.timestep[e], ts = p.path_len[e];
+    uint64_t ctr = p.ctr[e];
+
+    int pass = (p.mode == 1) ? 1 : 0;  // pass 1 = reset pass: fresh draws, zero action, obs only
+    V2 act_next;
+    act_next.x = 0; act_next.y = 0;
+    if (p.mode == 0 && lane < p.Np) act_next = reinterpret_cast<const V2*>(p.actions)[(size_t)e * p.Np + lane];
+
     for (int t = 0; t < p.T; ++t) {
-      for (int el = warp; el < n_loc; el += NW)
-        env_pre(p, env_slot(p, slots, el), e0 + el, t, false, lane);
-      __syncthreads();
-      for (int it = warp; it < n_items; it += NW) {
-        const int el = it / p.Np, pi = it - el * p.Np;
-        sense_item(p, env_slot(p, slots, el), sens, pi, lane,
-                   p.obs + (((size_t)t * p.E + e0 + el) * p.Np + pi) * p.D);
-      }
-      __syncthreads();
-      int need = 0;
-      for (int el = warp; el < n_loc; el += NW) {
-        const EnvSlot<real> s = env_slot(p, slots, el);
-        env_post(p, s, e0 + el, t, false, lane);
-        need |= s.meta[2];
-      }
-      if (p.auto_reset) {
-        // VecEnvExecutor.step: a done env is reset in place; its obs slot gets the reset obs
-        // (rllab/sandbox/rocky/tf/envs/vec_env_executor.py:24-27).
-        if (__syncthreads_or(need)) {
-          for (int el = warp; el < n_loc; el += NW) {
-            const EnvSlot<real> s = env_slot(p, slots, el);
-            if (s.meta[2]) { env_reset_draws(p, s, e0 + el, lane); env_pre(p, s, e0 + el, t, true, lane); }
+      V2 act = act_next;
+      if (p.mode == 0 && t + 1 < p.T && lane < p.Np)  // prefetch the next step's action
+        act_next = reinterpret_cast<const V2*>(p.actions)[((size_t)(t + 1) * p.E + e) * p.Np + lane];
+      bool need_reset;
+      do {
+        if (pass) {
+          // ---- reset draws, ww:144-170 (obstacle, pursuers, evaders, poisons) ----------------
+          tt = 0; ts = 0;
+          if (p.random_obstacle) {
+            SeqStream rs;
+            rs.init(p.seed, env_id, 0u, ctr);
+            obx = rs.next_unit<real>();
+            oby = rs.next_unit<real>();
+            ctr = rs.counter;
+          } else {
+            obx = p.obst_x; oby = p.obst_y;
           }
-          __syncthreads();
-          for (int it = warp; it < n_items; it += NW) {
-            const int el = it / p.Np, pi = it - el * p.Np;
-            const EnvSlot<real> s = env_slot(p, slots, el);
-            if (s.meta[2])
-              sense_item(p, s, sens, pi, lane, p.obs + (((size_t)t * p.E + e0 + el) * p.Np + pi) * p.D);
+          for (int o = 0; o < Nall; ++o) {
+            const bool oU = o < eLo, oE = !oU && o < eHi;
+            // ww:164,170 -- poisons also use ev_speed at reset
+            const Spawn<real> s = spawn_object<real>(p.seed, env_id, ctr, obx, oby,
+                                                     oU ? p.resp2_p : (oE ? p.resp2_e : p.resp2_po),
+                                                     p.ev_speed, oU ? 0 : 1);
+            ctr = s.ctr;
+#pragma unroll
+            for (int c = 0; c < OPL; ++c)
+              if (o == lane + 32 * c) { x[c] = s.x; y[c] = s.y; vx[c] = s.vx; vy[c] = s.vy; }
           }
-          __syncthreads();
-          for (int el = warp; el < n_loc; el += NW) {
-            const EnvSlot<real> s = env_slot(p, slots, el);
-            if (s.meta[2]) env_post(p, s, e0 + el, t, true, lane);
+          act.x = 0; act.y = 0;
+        }
+        // ---- integrate pursuers, control penalty, walls: ww:221-245 (pursuers = chunk 0) -------
+        real pen;
+        {
+          real sq = 0;
+          if (lane < p.Np) {
+            const real ax = act.x * p.action_scale, ay = act.y * p.action_scale;
+            vx[0] += ax; vy[0] += ay;
+            x[0] += vx[0]; y[0] += vy[0];
+            sq = ax * ax + ay * ay;
+            const real cx = clip01(x[0]), cy = clip01(y[0]);
+            if (x[0] != cx) vx[0] = 0;
+            if (y[0] != cy) vy[0] = 0;
+            x[0] = cx; y[0] = cy;
+          }
+          pen = p.control_penalty * (p.reward_global ? warp_sum(sq) : sq);
+        }
+        // ---- obstacle rebound (velocity only): ww:247-270 ----------------------------------------
+#pragma unroll
+        for (int c = 0; c < OPL; ++c) {
+          const real dx = x[c] - obx, dy = y[c] - oby;
+          if (dx * dx + dy * dy <= obst2_l[c]) { vx[c] = kf_l[c] * vx[c]; vy[c] = kf_l[c] * vy[c]; }
+        }
+        // ---- sense: one pursuer at a time -----------------------------------------------------
+        real* obs_env = p.obs + (((size_t)(p.mode == 1 ? 0 : t) * p.E + e) * p.Np) * p.D;
+        for (int pi = 0; pi < p.Np; ++pi) {
+          const real mx = __shfl_sync(FULL_MASK, x[0], pi), my = __shfl_sync(FULL_MASK, y[0], pi);
+          const real mvx = __shfl_sync(FULL_MASK, vx[0], pi), mvy = __shfl_sync(FULL_MASK, vy[0], pi);
+          // lanes as objects: geometry, collisions (ww:278-293), conservative range cull
+          real rx[OPL], ry[OPL], d2[OPL];
+          unsigned cm[OPL];
+          unsigned hitE = 0u, hitP = 0u;
+#pragma unroll
+          for (int c = 0; c < OPL; ++c) {
+            rx[c] = x[c] - mx; ry[c] = y[c] - my;
+            d2[c] = rx[c] * rx[c] + ry[c] * ry[c];
+            cm[c] = __ballot_sync(FULL_MASK, d2[c] <= cull2_l[c]);
+            const bool hit = d2[c] <= coll2_l[c];
+            const unsigned hb = __ballot_sync(FULL_MASK, hit);
+            if (hit) col[c] |= 1u << pi;
+            hitE |= hb & mE[c];
+            hitP |= hb & mP[c];
+          }
+          cm[0] &= ~(1u << pi);  // ww:70-71 `same`
+          const real orx = obx - mx, ory = oby - my;
+          const real od2 = orx * orx + ory * ory;
+          real* obs_row = obs_env + (size_t)pi * p.D;
+#pragma unroll
+          for (int kc = 0; kc < KCH; ++kc) {
+            const real sx = sx_l[kc], sy = sy_l[kc];
+            // lanes as sensors: nearest sensed object per class (ww:64-72, 312-334)
+            real bO = INF, bE = INF, bP = INF, bU = INF;
+            int iE = 0, iP = 0, iU = 0;
+            if (od2 <= p.cull2) {
+              const real sv = sx * orx + sy * ory;
+              const bool ok = !((sv < (real)0) | (sv > p.range) | (od2 - sv * sv > p.r_p2));
+              bO = ok ? sv : INF;
+            }
+#pragma unroll
+            for (int c = 0; c < OPL; ++c) {
+#define MADRL_WW_SCAN(MASK, BEST, IDX)                                                      \
+  for (unsigned m = cm[c] & (MASK); m != 0u; m &= m - 1u) {                                  \
+    const int j = __ffs(m) - 1;                                                              \
+    const real jx = __shfl_sync(FULL_MASK, rx[c], j), jy = __shfl_sync(FULL_MASK, ry[c], j); \
+    const real jd = __shfl_sync(FULL_MASK, d2[c], j);                                        \
+    const real sv = sx * jx + sy * jy;                                                       \
+    const bool ok = !((sv < (real)0) | (sv > p.range) | (jd - sv * sv > p.r_p2));            \
+    if (ok && sv < BEST) { BEST = sv; IDX = j + 32 * c; }                                    \
+  }
+              MADRL_WW_SCAN(mU[c], bU, iU)
+              MADRL_WW_SCAN(mE[c], bE, iE)
+              MADRL_WW_SCAN(mP[c], bP, iP)
+#undef MADRL_WW_SCAN
+            }
+            // features ww:312-353, 388-395: feature-major, sensor-minor
+            const int k = lane + 32 * kc;
+            const bool hO = bO < INF, hE = bE < INF, hP = bP < INF, hU = bU < INF;
+            const real z = (real)0;
+            if (p.speed_features) {
+              real oEx = z, oEy = z, oPx = z, oPy = z, oUx = z, oUy = z;
+#pragma unroll
+              for (int c = 0; c < OPL; ++c) {
+                const real ex_ = __shfl_sync(FULL_MASK, vx[c], iE & 31), ey_ = __shfl_sync(FULL_MASK, vy[c], iE & 31);
+                const real px_ = __shfl_sync(FULL_MASK, vx[c], iP & 31), py_ = __shfl_sync(FULL_MASK, vy[c], iP & 31);
+                const real ux_ = __shfl_sync(FULL_MASK, vx[c], iU & 31), uy_ = __shfl_sync(FULL_MASK, vy[c], iU & 31);
+                if ((iE >> 5) == c) { oEx = ex_; oEy = ey_; }
+                if ((iP >> 5) == c) { oPx = px_; oPy = py_; }
+                if ((iU >> 5) == c) { oUx = ux_; oUy = uy_; }
+              }
+              if (k < p.K) {
+                store_stream(obs_row + 0 * p.K + k, hO ? bO : z);
+                store_stream(obs_row + 1 * p.K + k, hE ? bE : z);
+                store_stream(obs_row + 2 * p.K + k, hE ? sx * (oEx - mvx) + sy * (oEy - mvy) : z);
+                store_stream(obs_row + 3 * p.K + k, hP ? bP : z);
+                store_stream(obs_row + 4 * p.K + k, hP ? sx * (oPx - mvx) + sy * (oPy - mvy) : z);
+                store_stream(obs_row + 5 * p.K + k, hU ? bU : z);
+                store_stream(obs_row + 6 * p.K + k, hU ? sx * (oUx - mvx) + sy * (oUy - mvy) : z);
+              }
+            } else if (k < p.K) {
+              store_stream(obs_row + 0 * p.K + k, hO ? bO : z);
+              store_stream(obs_row + 1 * p.K + k, hE ? bE : z);
+              store_stream(obs_row + 2 * p.K + k, hP ? bP : z);
+              store_stream(obs_row + 3 * p.K + k, hU ? bU : z);
+            }
+          }
+          // ww:411-428 tail: collided-with-evader, collided-with-poison, id
+          real* tail = obs_row + n_feat * p.K;
+          if (lane == 0) store_stream(tail, hitE ? (real)1 : (real)0);
+          if (lane == 1) store_stream(tail + 1, hitP ? (real)1 : (real)0);
+          if (lane == 2 && p.addid) store_stream(tail + 2, (real)(pi + 1));
+        }
+        // ---- catches, respawn, rewards: ww:285,293,358-385 -----------------------------------------
+        unsigned whoE = 0u, whoP = 0u, whoEnc = 0u;
+        int nE = 0, nP = 0, nEnc = 0;
+#pragma unroll
+        for (int c = 0; c < OPL; ++c) {
+          const int cnt = __popc(col[c]);
+          const bool caught = cnt >= need_l[c];
+          const unsigned cmk = __ballot_sync(FULL_MASK, caught);
+          const unsigned enc = __ballot_sync(FULL_MASK, cnt >= 1) & mE[c];   // ww:376
+          nE += __popc(cmk & mE[c]);
+          nP += __popc(cmk & mP[c]);
+          nEnc += __popc(enc);
+          if (caught) { if ((mE[c] >> lane) & 1u) whoE |= col[c]; else whoP |= col[c]; }
+          if ((enc >> lane) & 1u) whoEnc |= col[c];
+          col[c] = 0u;
+          for (unsigned m = cmk; m != 0u; m &= m - 1u) {   // ascending index: evaders, then poisons
+            const int j = __ffs(m) - 1;
+            const bool jE = (mE[c] >> j) & 1u;
+            const Spawn<real> s = spawn_object<real>(p.seed, env_id, ctr, obx, oby,
+                                                     jE ? p.resp2_e : p.resp2_po,
+                                                     jE ? p.ev_speed : p.poison_speed, 1);
+            ctr = s.ctr;
+            if (lane == j) { x[c] = s.x; y[c] = s.y; vx[c] = s.vx; vy[c] = s.vy; }
           }
         }
-      }
+        whoE = __reduce_or_sync(FULL_MASK, whoE);
+        whoP = __reduce_or_sync(FULL_MASK, whoP);
+        whoEnc = __reduce_or_sync(FULL_MASK, whoEnc);
+        if (!pass && lane < p.Np) {
+          real r = pen;
+          if (p.reward_global) {
+            r += ((real)nE * p.food_reward + (real)nP * p.poison_reward) + (real)nEnc * p.encounter_reward;
+          } else {   // fancy-index += : at most once per category (ww:383-385)
+            if ((whoE >> lane) & 1u) r += p.food_reward;
+            if ((whoP >> lane) & 1u) r += p.poison_reward;
+            if ((whoEnc >> lane) & 1u) r += p.encounter_reward;
+          }
+          store_stream(p.rew + ((size_t)t * p.E + e) * p.Np + lane, r);
+        }
+        // ---- evaders / poison drift; bounce only if BOTH coordinates left [0,1]: ww:397-409 ---------
+#pragma unroll
+        for (int c = 0; c < OPL; ++c) {
+          if (((mE[c] | mP[c]) >> lane) & 1u) {
+            x[c] += vx[c]; y[c] += vy[c];
+            const bool ox = (x[c] < (real)0) || (x[c] > (real)1), oy = (y[c] < (real)0) || (y[c] > (real)1);
+            if (ox && oy) { vx[c] = -vx[c]; vy[c] = -vy[c]; }
+          }
+        }
+        // ---- bookkeeping ww:433-436 + VecEnvExecutor horizon ---------------------------------------
+        tt += 1;
+        need_reset = false;
+        if (!pass) {
+          ts += 1;
+          const bool done = (tt >= p.timestep_limit) || (p.max_path_length > 0 && ts >= p.max_path_length);
+          if (lane == 0) {
+            p.done[(size_t)t * p.E + e] = done ? 1 : 0;
+            reinterpret_cast<int2*>(p.info)[(size_t)t * p.E + e] = make_int2(nE, nP);
+          }
+          // VecEnvExecutor.step: a done env is reset in place and its obs slot receives the
+          // reset observation (rllab/sandbox/rocky/tf/envs/vec_env_executor.py:24-27)
+          need_reset = done && p.auto_reset;
+        }
+        pass = need_reset ? 1 : 0;
+      } while (need_reset);
     }
-  }
-  __syncthreads();
-
-  // ---- write state back ---------------------------------------------------------------------
-  for (int i = tid; i < n_loc * p.Nall; i += blockDim.x) {
-    const int el = i % n_loc, o = i / n_loc;
-    const EnvSlot<real> s = env_slot(p, slots, el);
-    const size_t g = (size_t)o * p.E + e0 + el;
-    p.pos_x[g] = s.px[o]; p.pos_y[g] = s.py[o]; p.vel_x[g] = s.vx[o]; p.vel_y[g] = s.vy[o];
-  }
-  for (int el = tid; el < n_loc; el += blockDim.x) {
-    const EnvSlot<real> s = env_slot(p, slots, el);
-    p.obst_px[e0 + el] = s.px[p.Nall];
-    p.obst_py[e0 + el] = s.py[p.Nall];
-    p.timestep[e0 + el] = s.meta[0];
-    p.path_len[e0 + el] = s.meta[1];
-    p.ctr[e0 + el] = *s.ctr;
+    // ---- registers -> HBM record ------------------------------------------------------------------
+#pragma unroll
+    for (int c = 0; c < OPL; ++c) {
+      const int o = lane + 32 * c;
+      if (o < Nall) { rec[o] = x[c]; rec[Nall + o] = y[c]; rec[2 * Nall + o] = vx[c]; rec[3 * Nall + o] = vy[c]; }
+    }
+    if (lane == 0) {
+      p.obst[2 * (size_t)e] = obx; p.obst[2 * (size_t)e + 1] = oby;
+      p.timestep[e] = tt; p.path_len[e] = ts; p.ctr[e] = ctr;
+    }
   }
 }
 
@@ -476,7 +403,9 @@ static int ww_validate(const madrl_ww_config* c) {
   MADRL_REQUIRE(c->n_pursuers >= 1 && c->n_pursuers <= 32,
                 "n_pursuers must be in [1,32] (collision rows are 32-bit masks), got %d", c->n_pursuers);
   MADRL_REQUIRE(c->n_evaders >= 1 && c->n_poison >= 1, "n_evaders and n_poison must be >= 1");
-  MADRL_REQUIRE(c->n_sensors >= 1 && c->n_sensors <= 1024, "n_sensors out of range");
+  MADRL_REQUIRE(c->n_sensors >= 1 && c->n_sensors <= 64, "n_sensors must be in [1,64], got %d", c->n_sensors);
+  MADRL_REQUIRE(c->n_pursuers + c->n_evaders + c->n_poison <= 256,
+                "n_pursuers + n_evaders + n_poison must be <= 256 (8 objects per lane)");
   MADRL_REQUIRE(c->n_coop >= 1, "n_coop must be >= 1");
   MADRL_REQUIRE(c->timestep_limit >= 1, "timestep_limit must be >= 1");
   return MADRL_OK;
@@ -491,12 +420,8 @@ extern "C" int madrl_ww_state_layout(const madrl_ww_config* c, madrl_ww_layout* 
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   out->rng_counter = take(8 * E);
-  out->pos_x = take(rb * nobj * E);
-  out->pos_y = take(rb * nobj * E);
-  out->vel_x = take(rb * nobj * E);
-  out->vel_y = take(rb * nobj * E);
-  out->obst_x = take(rb * E);
-  out->obst_y = take(rb * E);
+  out->objs = take(rb * 4 * nobj * E);
+  out->obst = take(rb * 2 * E);
   out->timestep = take(4 * E);
   out->path_len = take(4 * E);
   out->sensors = take(rb * 2 * (size_t)c->n_sensors);
@@ -579,10 +504,37 @@ extern "C" int madrl_ww_seed(madrl_ww* h, uint64_t seed, void* stream) {
 
 extern "C" int madrl_ww_set_launch(madrl_ww* h, int warps_per_block, int blocks_per_sm) {
   MADRL_REQUIRE(h != nullptr, "handle is NULL");
-  MADRL_REQUIRE(warps_per_block >= 0 && warps_per_block <= 16, "warps_per_block must be in [0,16]");
+  MADRL_REQUIRE(warps_per_block >= 0 && warps_per_block <= 4, "warps_per_block must be in [0,4]");
   MADRL_REQUIRE(blocks_per_sm >= 0 && blocks_per_sm <= 32, "blocks_per_sm must be in [0,32]");
   h->warps_per_block = warps_per_block;
   h->blocks_per_sm = blocks_per_sm;
+  return MADRL_OK;
+}
+
+// Largest representable t with correctly-rounded sqrt(t) <= thr: `sqrt(d2) <= thr` (what
+// scipy's cdist + `<=` computes in the reference) is then exactly `d2 <= t`.
+template <typename real>
+static real exact_sq_threshold(double thr_d) {
+  const real thr = (real)thr_d;
+  real t = thr * thr;
+  const real up = (real)INFINITY, dn = -(real)INFINITY;
+  while (std::sqrt(t) <= thr) t = std::nextafter(t, up);
+  while (std::sqrt(t) > thr) t = std::nextafter(t, dn);
+  return t;
+}
+
+template <typename real, int OPL, int KCH>
+static int ww_launch_inst(madrl_ww* h, const WWParams<real>& p, cudaStream_t stream) {
+  const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 4;
+  int resident = 0;
+  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ww_kernel<real, OPL, KCH>, wpb * 32, 0));
+  if (resident < 1) resident = 1;
+  if (h->blocks_per_sm > 0 && h->blocks_per_sm < resident) resident = h->blocks_per_sm;
+  int grid = (p.E + wpb - 1) / wpb;                  // one warp per env ...
+  if (grid > h->sms * resident) grid = h->sms * resident;  // ... or a single persistent wave
+  ww_kernel<real, OPL, KCH><<<grid, wpb * 32, 0, stream>>>(p);
+  g_launches.fetch_add(1);
+  MADRL_CUDA_CHECK(cudaGetLastError());
   return MADRL_OK;
 }
 
@@ -595,7 +547,6 @@ static int ww_launch(madrl_ww* h, int mode, int T, const void* actions, void* ob
   p.E = c.n_envs; p.env_id_base = c.env_id_base;
   p.Np = c.n_pursuers; p.Ne = c.n_evaders; p.Npo = c.n_poison; p.K = c.n_sensors;
   p.n_coop = c.n_coop; p.D = h->lay.obs_dim; p.Nall = h->lay.n_obj;
-  p.CW = (p.Nall + 1 + 31) / 32;
   p.reward_global = c.reward_global; p.addid = c.addid; p.speed_features = c.speed_features;
   p.random_obstacle = c.random_obstacle; p.timestep_limit = c.timestep_limit;
   p.max_path_length = c.max_path_length;
@@ -606,14 +557,14 @@ static int ww_launch(madrl_ww* h, int mode, int T, const void* actions, void* ob
   p.range = (real)c.sensor_range;
   // Exact conservative cull: sv <= range and d2 - sv^2 <= r^2 imply d2 <= range^2 + r^2.
   p.cull2 = (real)((c.sensor_range * c.sensor_range + r_p * r_p) * (1.0 + 1e-4) + 1e-12);
-  p.rsum_e = (real)(r_p + r_e);
-  p.rsum_po = (real)(r_p + r_po);
-  p.thr_obst_p = (real)(r_p + c.obstacle_radius);
-  p.thr_obst_e = (real)(r_e + c.obstacle_radius);
-  p.thr_obst_po = (real)(r_po + c.obstacle_radius);
-  p.thr_resp_p = (real)(r_p * 2 + c.obstacle_radius);
-  p.thr_resp_e = (real)(r_e * 2 + c.obstacle_radius);
-  p.thr_resp_po = (real)(r_po * 2 + c.obstacle_radius);
+  p.coll2_e = exact_sq_threshold<real>(r_p + r_e);
+  p.coll2_po = exact_sq_threshold<real>(r_p + r_po);
+  p.obst2_p = exact_sq_threshold<real>(r_p + c.obstacle_radius);
+  p.obst2_e = exact_sq_threshold<real>(r_e + c.obstacle_radius);
+  p.obst2_po = exact_sq_threshold<real>(r_po + c.obstacle_radius);
+  p.resp2_p = exact_sq_threshold<real>(r_p * 2 + c.obstacle_radius);
+  p.resp2_e = exact_sq_threshold<real>(r_e * 2 + c.obstacle_radius);
+  p.resp2_po = exact_sq_threshold<real>(r_po * 2 + c.obstacle_radius);
   p.obst_x = (real)c.obstacle_x; p.obst_y = (real)c.obstacle_y;
   p.ev_speed = (real)c.ev_speed; p.poison_speed = (real)c.poison_speed;
   p.action_scale = (real)c.action_scale;
@@ -621,43 +572,28 @@ static int ww_launch(madrl_ww* h, int mode, int T, const void* actions, void* ob
   p.encounter_reward = (real)c.encounter_reward; p.control_penalty = (real)c.control_penalty;
   p.seed = c.seed;
   char* st = h->state;
-  p.pos_x = (real*)(st + h->lay.pos_x); p.pos_y = (real*)(st + h->lay.pos_y);
-  p.vel_x = (real*)(st + h->lay.vel_x); p.vel_y = (real*)(st + h->lay.vel_y);
-  p.obst_px = (real*)(st + h->lay.obst_x); p.obst_py = (real*)(st + h->lay.obst_y);
+  p.objs = (real*)(st + h->lay.objs);
+  p.obst = (real*)(st + h->lay.obst);
   p.timestep = (int32_t*)(st + h->lay.timestep); p.path_len = (int32_t*)(st + h->lay.path_len);
   p.ctr = (uint64_t*)(st + h->lay.rng_counter);
   p.sensors = (const real*)(st + h->lay.sensors);
   p.actions = (const real*)actions; p.obs = (real*)obs; p.rew = (real*)rew;
   p.done = done; p.info = info; p.mask = mask;
 
-  // launch geometry: persistent blocks, contiguous env ranges, SM-balanced
-  const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 8;
-  const int bps = h->blocks_per_sm > 0 ? h->blocks_per_sm : 8;
-  int grid = h->sms * bps;
-  if (grid > p.E) grid = p.E;
-  p.max_loc = (p.E + grid - 1) / grid;
-  // smem slot layout
-  size_t off = 0;
-  const size_t rb = sizeof(real);
-  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 8); return o; };
-  take(rb * (p.Nall + 1));                        // px (+ obstacle)
-  p.off_py = (int)take(rb * (p.Nall + 1));
-  p.off_vx = (int)take(rb * p.Nall);
-  p.off_vy = (int)take(rb * p.Nall);
-  p.off_rew = (int)take(rb * p.Np);
-  p.off_coll = (int)take(4 * (size_t)p.Np * p.CW);
-  p.off_meta = (int)take(4 * 4);
-  p.off_ctr = (int)take(8);
-  p.env_stride = (int)align_up(off, 16);
-  const size_t smem = align_up(2 * (size_t)p.K * rb, 16) + (size_t)p.max_loc * p.env_stride;
-  MADRL_REQUIRE(smem <= 200 * 1024, "env batch per block needs %zu B of shared memory", smem);
-  if (smem > 48 * 1024) {
-    MADRL_CUDA_CHECK(cudaFuncSetAttribute(ww_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int opl = (p.Nall + 31) / 32, kch = (p.K + 31) / 32;
+#define MADRL_WW_CASE(O, K_) return ww_launch_inst<real, O, K_>(h, p, stream)
+  if (kch == 1) {
+    if (opl == 1) MADRL_WW_CASE(1, 1);
+    if (opl == 2) MADRL_WW_CASE(2, 1);
+    if (opl <= 4) MADRL_WW_CASE(4, 1);
+    MADRL_WW_CASE(8, 1);
+  } else {
+    if (opl == 1) MADRL_WW_CASE(1, 2);
+    if (opl == 2) MADRL_WW_CASE(2, 2);
+    if (opl <= 4) MADRL_WW_CASE(4, 2);
+    MADRL_WW_CASE(8, 2);
   }
-  ww_kernel<real><<<grid, wpb * 32, smem, stream>>>(p);
-  g_launches.fetch_add(1);
-  MADRL_CUDA_CHECK(cudaGetLastError());
-  return MADRL_OK;
+#undef MADRL_WW_CASE
 }
 
 extern "C" int madrl_ww_reset(madrl_ww* h, const uint8_t* mask_dev, void* obs_dev, void* stream) {

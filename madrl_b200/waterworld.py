@@ -104,12 +104,13 @@ class BatchedMAWaterWorld(object):
 
     @property
     def state(self):
-        """Named views into the HBM state blob (struct-of-arrays, env index minor)."""
+        """Named views into the HBM state blob (one record per env)."""
         L, E, N, dt = self.layout, self.n_envs, self.n_obj, self.dtype
+        objs = self._view(L.objs, dt, (E, 4, N))
+        obst = self._view(L.obst, dt, (E, 2))
         return dict(
-            pos_x=self._view(L.pos_x, dt, (N, E)), pos_y=self._view(L.pos_y, dt, (N, E)),
-            vel_x=self._view(L.vel_x, dt, (N, E)), vel_y=self._view(L.vel_y, dt, (N, E)),
-            obst_x=self._view(L.obst_x, dt, (E,)), obst_y=self._view(L.obst_y, dt, (E,)),
+            pos_x=objs[:, 0], pos_y=objs[:, 1], vel_x=objs[:, 2], vel_y=objs[:, 3],
+            obst_x=obst[:, 0], obst_y=obst[:, 1],
             timestep=self._view(L.timestep, torch.int32, (E,)),
             path_len=self._view(L.path_len, torch.int32, (E,)),
             rng_counter=self._view(L.rng_counter, torch.int64, (E,)),

@@ -246,8 +246,8 @@ def fragile_step(o, state, action, eps):
             svm = np.where(hi, np.inf, sv)
             if svm.shape[1] >= 2:
                 part = np.sort(svm, axis=1)
-                gap = part[:, 1] - part[:, 0]
-                if np.any(np.isfinite(part[:, 1]) & (gap < eps)):
+                two = np.isfinite(part[:, 1])
+                if np.any(part[two, 1] - part[two, 0] < eps):
                     return True
     ex2 = ex + ev
     ox2 = ox + ov

@@ -35,8 +35,7 @@ def test_waterworld_layout_is_host_only_and_sane():
     lay = _lib.WWLayout()
     assert lib.madrl_ww_state_layout(C.byref(cfg), C.byref(lay)) == 0
     assert lay.obs_dim == 213 and lay.n_obj == 20 and lay.real_bytes == 4
-    offs = [lay.rng_counter, lay.pos_x, lay.pos_y, lay.vel_x, lay.vel_y, lay.obst_x, lay.obst_y,
-            lay.timestep, lay.path_len, lay.sensors]
+    offs = [lay.rng_counter, lay.objs, lay.obst, lay.timestep, lay.path_len, lay.sensors]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs) and lay.total_bytes > offs[-1]
     bad = _lib.WWConfig(n_envs=4, n_pursuers=40, n_evaders=5, n_poison=10, n_sensors=30, n_coop=2,
                         timestep_limit=1000)

@@ -21,7 +21,7 @@ from oracle.waterworld_oracle import WaterworldOracle, fragile_step
 pytestmark = pytest.mark.gpu
 
 TOL32 = 1e-5
-EPS_FRAGILE = 2e-6
+EPS_FRAGILE = 3e-7
 
 
 def make(cfg, E, dtype, **kw):
@@ -32,8 +32,8 @@ def make(cfg, E, dtype, **kw):
 def engine_state(eng, e):
     st = {k: v.cpu().numpy() for k, v in eng.state.items()}
     Np, Ne = eng.n_pursuers, eng.n_evaders
-    X = np.stack([st['pos_x'][:, e], st['pos_y'][:, e]], 1).astype(np.float64)
-    V = np.stack([st['vel_x'][:, e], st['vel_y'][:, e]], 1).astype(np.float64)
+    X = np.stack([st['pos_x'][e], st['pos_y'][e]], 1).astype(np.float64)
+    V = np.stack([st['vel_x'][e], st['vel_y'][e]], 1).astype(np.float64)
     return dict(px=X[:Np], pv=V[:Np], ex=X[Np:Np + Ne], ev=V[Np:Np + Ne], ox=X[Np + Ne:],
                 ov=V[Np + Ne:], obst=np.array([[st['obst_x'][e], st['obst_y'][e]]], dtype=np.float64),
                 t=int(st['timestep'][e]), counter=int(st['rng_counter'][e]))
@@ -169,7 +169,7 @@ def test_sharding_is_invisible_and_launch_geometry_is_irrelevant():
     half = E // 2
     for base in (0, half):
         sh = make(cfg, half, torch.float32, seed=7, env_id_base=base)
-        sh.set_launch(warps_per_block=3, blocks_per_sm=1)
+        sh.set_launch(warps_per_block=3, blocks_per_sm=1)  # multi-env-per-warp path
         sh.reset()
         out = [x.cpu() for x in sh.rollout(act[:, base:base + half].contiguous())]
         for a, b in zip(ref, out):
