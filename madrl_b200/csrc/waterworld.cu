@@ -96,10 +96,14 @@ __device__ __noinline__ Spawn<real> spawn_object(uint64_t seed, uint32_t env_id,
   return s;
 }
 
-template <typename real, int OPL, int KCH>
+// OPL = objects per lane (ceil(n_obj / 32)); KCH = sensors per lane (ceil(K / 32));
+// KC = compile-time sensor count (0 = runtime p.K): with KC known the 7 feature-row stores of a
+// pursuer use immediate offsets from one running pointer instead of 64-bit address arithmetic.
+template <typename real, int OPL, int KCH, int KC>
 __global__ void __launch_bounds__(128, (OPL <= 2 ? 7 : 4))
 ww_kernel(const __grid_constant__ WWParams<real> p) {
   const real INF = real_inf<real>();
+  const int K = KC > 0 ? KC : p.K;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -127,10 +131,12 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
 #pragma unroll
   for (int kc = 0; kc < KCH; ++kc) {
     const int k = lane + 32 * kc;
-    sx_l[kc] = (k < p.K) ? p.sensors[k] : (real)0;
-    sy_l[kc] = (k < p.K) ? p.sensors[p.K + k] : (real)0;
+    sx_l[kc] = (k < K) ? p.sensors[k] : (real)0;
+    sy_l[kc] = (k < K) ? p.sensors[K + k] : (real)0;
   }
   const int n_feat = p.speed_features ? 7 : 4;
+  const int n_tail = 2 + (p.addid ? 1 : 0);
+  const size_t step_stride = (size_t)p.E * p.Np * p.D;   // obs elements per lockstep step
   typedef typename Vec2<real>::type V2;
 
   for (int e = warp_global; e < p.E; e += warp_stride) {
@@ -154,6 +160,10 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     int tt = p.timestep[e], ts = p.path_len[e];
     uint64_t ctr = p.ctr[e];
 
+    // running output pointers (this lane's column of the env's first pursuer row at step t)
+    real* obs_t = p.obs + (size_t)e * p.Np * p.D + lane;
+    real* rew_t = p.rew + (size_t)e * p.Np + lane;
+    size_t te = (size_t)e;   // index of (t, e) in the [T][E] done / info tensors
     int pass = (p.mode == 1) ? 1 : 0;  // pass 1 = reset pass: fresh draws, zero action, obs only
     V2 act_next;
     act_next.x = 0; act_next.y = 0;
@@ -213,8 +223,8 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
           if (dx * dx + dy * dy <= obst2_l[c]) { vx[c] = kf_l[c] * vx[c]; vy[c] = kf_l[c] * vy[c]; }
         }
         // ---- sense: one pursuer at a time -----------------------------------------------------
-        real* obs_env = p.obs + (((size_t)(p.mode == 1 ? 0 : t) * p.E + e) * p.Np) * p.D;
-        for (int pi = 0; pi < p.Np; ++pi) {
+        real* obs_row = obs_t;
+        for (int pi = 0; pi < p.Np; ++pi, obs_row += p.D) {
           const real mx = __shfl_sync(FULL_MASK, x[0], pi), my = __shfl_sync(FULL_MASK, y[0], pi);
           const real mvx = __shfl_sync(FULL_MASK, vx[0], pi), mvy = __shfl_sync(FULL_MASK, vy[0], pi);
           // lanes as objects: geometry, collisions (ww:278-293), conservative range cull
@@ -235,7 +245,6 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
           cm[0] &= ~(1u << pi);  // ww:70-71 `same`
           const real orx = obx - mx, ory = oby - my;
           const real od2 = orx * orx + ory * ory;
-          real* obs_row = obs_env + (size_t)pi * p.D;
 #pragma unroll
           for (int kc = 0; kc < KCH; ++kc) {
             const real sx = sx_l[kc], sy = sy_l[kc];
@@ -267,38 +276,47 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
             const int k = lane + 32 * kc;
             const bool hO = bO < INF, hE = bE < INF, hP = bP < INF, hU = bU < INF;
             const real z = (real)0;
+            real* o = obs_row + 32 * kc;   // this lane's column
             if (p.speed_features) {
-              real oEx = z, oEy = z, oPx = z, oPy = z, oUx = z, oUy = z;
+              real oEx, oEy, oPx, oPy, oUx, oUy;
+              if (OPL == 1) {
+                oEx = __shfl_sync(FULL_MASK, vx[0], iE); oEy = __shfl_sync(FULL_MASK, vy[0], iE);
+                oPx = __shfl_sync(FULL_MASK, vx[0], iP); oPy = __shfl_sync(FULL_MASK, vy[0], iP);
+                oUx = __shfl_sync(FULL_MASK, vx[0], iU); oUy = __shfl_sync(FULL_MASK, vy[0], iU);
+              } else {
+                oEx = oEy = oPx = oPy = oUx = oUy = z;
 #pragma unroll
-              for (int c = 0; c < OPL; ++c) {
-                const real ex_ = __shfl_sync(FULL_MASK, vx[c], iE & 31), ey_ = __shfl_sync(FULL_MASK, vy[c], iE & 31);
-                const real px_ = __shfl_sync(FULL_MASK, vx[c], iP & 31), py_ = __shfl_sync(FULL_MASK, vy[c], iP & 31);
-                const real ux_ = __shfl_sync(FULL_MASK, vx[c], iU & 31), uy_ = __shfl_sync(FULL_MASK, vy[c], iU & 31);
-                if ((iE >> 5) == c) { oEx = ex_; oEy = ey_; }
-                if ((iP >> 5) == c) { oPx = px_; oPy = py_; }
-                if ((iU >> 5) == c) { oUx = ux_; oUy = uy_; }
+                for (int c = 0; c < OPL; ++c) {
+                  const real ex_ = __shfl_sync(FULL_MASK, vx[c], iE & 31), ey_ = __shfl_sync(FULL_MASK, vy[c], iE & 31);
+                  const real px_ = __shfl_sync(FULL_MASK, vx[c], iP & 31), py_ = __shfl_sync(FULL_MASK, vy[c], iP & 31);
+                  const real ux_ = __shfl_sync(FULL_MASK, vx[c], iU & 31), uy_ = __shfl_sync(FULL_MASK, vy[c], iU & 31);
+                  if ((iE >> 5) == c) { oEx = ex_; oEy = ey_; }
+                  if ((iP >> 5) == c) { oPx = px_; oPy = py_; }
+                  if ((iU >> 5) == c) { oUx = ux_; oUy = uy_; }
+                }
               }
-              if (k < p.K) {
-                store_stream(obs_row + 0 * p.K + k, hO ? bO : z);
-                store_stream(obs_row + 1 * p.K + k, hE ? bE : z);
-                store_stream(obs_row + 2 * p.K + k, hE ? sx * (oEx - mvx) + sy * (oEy - mvy) : z);
-                store_stream(obs_row + 3 * p.K + k, hP ? bP : z);
-                store_stream(obs_row + 4 * p.K + k, hP ? sx * (oPx - mvx) + sy * (oPy - mvy) : z);
-                store_stream(obs_row + 5 * p.K + k, hU ? bU : z);
-                store_stream(obs_row + 6 * p.K + k, hU ? sx * (oUx - mvx) + sy * (oUy - mvy) : z);
+              if (k < K) {
+                store_stream(o + 0 * K, hO ? bO : z);
+                store_stream(o + 1 * K, hE ? bE : z);
+                store_stream(o + 2 * K, hE ? sx * (oEx - mvx) + sy * (oEy - mvy) : z);
+                store_stream(o + 3 * K, hP ? bP : z);
+                store_stream(o + 4 * K, hP ? sx * (oPx - mvx) + sy * (oPy - mvy) : z);
+                store_stream(o + 5 * K, hU ? bU : z);
+                store_stream(o + 6 * K, hU ? sx * (oUx - mvx) + sy * (oUy - mvy) : z);
               }
-            } else if (k < p.K) {
-              store_stream(obs_row + 0 * p.K + k, hO ? bO : z);
-              store_stream(obs_row + 1 * p.K + k, hE ? bE : z);
-              store_stream(obs_row + 2 * p.K + k, hP ? bP : z);
-              store_stream(obs_row + 3 * p.K + k, hU ? bU : z);
+            } else if (k < K) {
+              store_stream(o + 0 * K, hO ? bO : z);
+              store_stream(o + 1 * K, hE ? bE : z);
+              store_stream(o + 2 * K, hP ? bP : z);
+              store_stream(o + 3 * K, hU ? bU : z);
             }
           }
-          // ww:411-428 tail: collided-with-evader, collided-with-poison, id
-          real* tail = obs_row + n_feat * p.K;
-          if (lane == 0) store_stream(tail, hitE ? (real)1 : (real)0);
-          if (lane == 1) store_stream(tail + 1, hitP ? (real)1 : (real)0);
-          if (lane == 2 && p.addid) store_stream(tail + 2, (real)(pi + 1));
+          // ww:411-428 tail: collided-with-evader, collided-with-poison, id -- one store
+          if (lane < n_tail) {
+            const real tv = lane == 0 ? (hitE ? (real)1 : (real)0)
+                          : (lane == 1 ? (hitP ? (real)1 : (real)0) : (real)(pi + 1));
+            store_stream(obs_row + n_feat * K, tv);
+          }
         }
         // ---- catches, respawn, rewards: ww:285,293,358-385 -----------------------------------------
         unsigned whoE = 0u, whoP = 0u, whoEnc = 0u;
@@ -337,7 +355,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
             if ((whoP >> lane) & 1u) r += p.poison_reward;
             if ((whoEnc >> lane) & 1u) r += p.encounter_reward;
           }
-          store_stream(p.rew + ((size_t)t * p.E + e) * p.Np + lane, r);
+          store_stream(rew_t, r);
         }
         // ---- evaders / poison drift; bounce only if BOTH coordinates left [0,1]: ww:397-409 ---------
 #pragma unroll
@@ -355,8 +373,8 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
           ts += 1;
           const bool done = (tt >= p.timestep_limit) || (p.max_path_length > 0 && ts >= p.max_path_length);
           if (lane == 0) {
-            p.done[(size_t)t * p.E + e] = done ? 1 : 0;
-            reinterpret_cast<int2*>(p.info)[(size_t)t * p.E + e] = make_int2(nE, nP);
+            p.done[te] = done ? 1 : 0;
+            reinterpret_cast<int2*>(p.info)[te] = make_int2(nE, nP);
           }
           // VecEnvExecutor.step: a done env is reset in place and its obs slot receives the
           // reset observation (rllab/sandbox/rocky/tf/envs/vec_env_executor.py:24-27)
@@ -364,6 +382,9 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
         }
         pass = need_reset ? 1 : 0;
       } while (need_reset);
+      obs_t += step_stride;
+      rew_t += (size_t)p.E * p.Np;
+      te += (size_t)p.E;
     }
     // ---- registers -> HBM record ------------------------------------------------------------------
 #pragma unroll
@@ -523,16 +544,16 @@ static real exact_sq_threshold(double thr_d) {
   return t;
 }
 
-template <typename real, int OPL, int KCH>
+template <typename real, int OPL, int KCH, int KC>
 static int ww_launch_inst(madrl_ww* h, const WWParams<real>& p, cudaStream_t stream) {
   const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 4;
   int resident = 0;
-  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ww_kernel<real, OPL, KCH>, wpb * 32, 0));
+  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ww_kernel<real, OPL, KCH, KC>, wpb * 32, 0));
   if (resident < 1) resident = 1;
   if (h->blocks_per_sm > 0 && h->blocks_per_sm < resident) resident = h->blocks_per_sm;
   int grid = (p.E + wpb - 1) / wpb;                  // one warp per env ...
   if (grid > h->sms * resident) grid = h->sms * resident;  // ... or a single persistent wave
-  ww_kernel<real, OPL, KCH><<<grid, wpb * 32, 0, stream>>>(p);
+  ww_kernel<real, OPL, KCH, KC><<<grid, wpb * 32, 0, stream>>>(p);
   g_launches.fetch_add(1);
   MADRL_CUDA_CHECK(cudaGetLastError());
   return MADRL_OK;
@@ -581,17 +602,22 @@ static int ww_launch(madrl_ww* h, int mode, int T, const void* actions, void* ob
   p.done = done; p.info = info; p.mask = mask;
 
   const int opl = (p.Nall + 31) / 32, kch = (p.K + 31) / 32;
-#define MADRL_WW_CASE(O, K_) return ww_launch_inst<real, O, K_>(h, p, stream)
-  if (kch == 1) {
-    if (opl == 1) MADRL_WW_CASE(1, 1);
-    if (opl == 2) MADRL_WW_CASE(2, 1);
-    if (opl <= 4) MADRL_WW_CASE(4, 1);
-    MADRL_WW_CASE(8, 1);
+#define MADRL_WW_CASE(O, KH, KC_) return ww_launch_inst<real, O, KH, KC_>(h, p, stream)
+  if (p.K == 30) {   // the reference's n_sensors default: compile-time K
+    if (opl == 1) MADRL_WW_CASE(1, 1, 30);
+    if (opl == 2) MADRL_WW_CASE(2, 1, 30);
+    if (opl <= 4) MADRL_WW_CASE(4, 1, 30);
+    MADRL_WW_CASE(8, 1, 30);
+  } else if (kch == 1) {
+    if (opl == 1) MADRL_WW_CASE(1, 1, 0);
+    if (opl == 2) MADRL_WW_CASE(2, 1, 0);
+    if (opl <= 4) MADRL_WW_CASE(4, 1, 0);
+    MADRL_WW_CASE(8, 1, 0);
   } else {
-    if (opl == 1) MADRL_WW_CASE(1, 2);
-    if (opl == 2) MADRL_WW_CASE(2, 2);
-    if (opl <= 4) MADRL_WW_CASE(4, 2);
-    MADRL_WW_CASE(8, 2);
+    if (opl == 1) MADRL_WW_CASE(1, 2, 0);
+    if (opl == 2) MADRL_WW_CASE(2, 2, 0);
+    if (opl <= 4) MADRL_WW_CASE(4, 2, 0);
+    MADRL_WW_CASE(8, 2, 0);
   }
 #undef MADRL_WW_CASE
 }
