@@ -112,6 +112,63 @@ int madrl_ww_reset_host(madrl_ww* h, const uint8_t* mask_host, void* obs_host);
 int madrl_ww_rollout_host(madrl_ww* h, int T, const void* actions_host, void* obs_host,
                           void* rew_host, uint8_t* done_host, int32_t* info_host, int auto_reset);
 
+/* ------------------------------------------------------------------ PursuitEvade ------------ */
+typedef struct madrl_pursuit_config {
+  int32_t n_envs, env_id_base;
+  int32_t n_pursuers, n_evaders;      /* pursuit_evade.py:60-61 (<= 32 / <= 64)                 */
+  int32_t xs, ys, n_maps;             /* map_pool shape (n_maps, xs, ys); -1 = building         */
+  int32_t obs_range;                  /* pursuit_evade.py:63                                     */
+  int32_t flatten;                    /* pursuit_evade.py:67 (1 only)                            */
+  int32_t n_catch, surround;          /* pursuit_evade.py:79,142                                 */
+  int32_t reward_global, include_id, sample_maps;
+  int32_t max_path_length;            /* VecEnvExecutor horizon, 0 = none                        */
+  int32_t _pad;
+  double layer_norm, catchr, term_pursuit, urgency_reward, constraint_window;
+  uint64_t seed;
+} madrl_pursuit_config;
+
+/* Byte offsets into the state blob (one record per env). */
+typedef struct madrl_pursuit_layout {
+  size_t total_bytes;
+  size_t pos;          /* uint8  [E][2][n_agents]  x row, y row; pursuers first, then evaders     */
+  size_t gone;         /* uint64 [E]  bit j: evader j has been removed (evaders_gone)             */
+  size_t map_id;       /* int32  [E]  index into the map pool                                     */
+  size_t path_len;     /* int32  [E]  VecEnvExecutor.ts                                           */
+  size_t rng_counter;  /* uint64 [E]                                                              */
+  size_t stale;        /* uint16 [E][Np][R*R]  the never-cleared channels 1-2 of local_obs
+                          (pursuit_evade.py:119,438): pursuer count | evader count << 8           */
+  size_t maps;         /* uint8  [n_maps][xs*ys] 1 = building (constant)                          */
+  size_t lut, idv;     /* float tables (constant)                                                 */
+  int32_t n_agents, obs_dim;
+} madrl_pursuit_layout;
+
+typedef struct madrl_pursuit madrl_pursuit;
+
+int madrl_pursuit_state_layout(const madrl_pursuit_config* cfg, madrl_pursuit_layout* out);
+/* map_pool_host: int32 [n_maps][xs][ys] (the .npy the reference loads, maps/map_pool16.npy). */
+int madrl_pursuit_create(const madrl_pursuit_config* cfg, const int32_t* map_pool_host,
+                         void* state_dev, madrl_pursuit** out);
+int madrl_pursuit_destroy(madrl_pursuit* h);
+void* madrl_pursuit_state_ptr(madrl_pursuit* h);
+int madrl_pursuit_seed(madrl_pursuit* h, uint64_t seed, void* stream);
+int madrl_pursuit_set_launch(madrl_pursuit* h, int warps_per_block, int blocks_per_sm);
+/* Curriculum knobs that survive pickling in the reference (pursuit_evade.py:264-272,397-411). */
+int madrl_pursuit_set_params(madrl_pursuit* h, double catchr, double constraint_window);
+/* reset(): obs_dev float [E][Np][obs_dim]. */
+int madrl_pursuit_reset(madrl_pursuit* h, const uint8_t* mask_dev, float* obs_dev, void* stream);
+/* actions_dev int32 [T][E][Np] in {0 left,1 right,2 up,3 down,4 stay} (DiscreteAgent.py:28-38);
+ * obs_dev float [T][E][Np][obs_dim]; rew_dev float [T][E][Np] (computed in float64, narrowed once);
+ * done_dev uint8 [T][E]; info_dev int32 [T][E] = removed. */
+int madrl_pursuit_rollout(madrl_pursuit* h, int T, const int32_t* actions_dev, float* obs_dev,
+                          float* rew_dev, uint8_t* done_dev, int32_t* info_dev, int auto_reset,
+                          void* stream);
+int madrl_pursuit_step(madrl_pursuit* h, const int32_t* actions_dev, float* obs_dev, float* rew_dev,
+                       uint8_t* done_dev, int32_t* info_dev, int auto_reset, void* stream);
+int madrl_pursuit_reset_host(madrl_pursuit* h, const uint8_t* mask_host, float* obs_host);
+int madrl_pursuit_rollout_host(madrl_pursuit* h, int T, const int32_t* actions_host, float* obs_host,
+                               float* rew_host, uint8_t* done_host, int32_t* info_host,
+                               int auto_reset);
+
 #ifdef __cplusplus
 }
 #endif

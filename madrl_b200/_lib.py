@@ -40,6 +40,27 @@ class WWLayout(C.Structure):
     ]
 
 
+class PEConfig(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32), ("env_id_base", C.c_int32), ("n_pursuers", C.c_int32),
+        ("n_evaders", C.c_int32), ("xs", C.c_int32), ("ys", C.c_int32), ("n_maps", C.c_int32),
+        ("obs_range", C.c_int32), ("flatten", C.c_int32), ("n_catch", C.c_int32),
+        ("surround", C.c_int32), ("reward_global", C.c_int32), ("include_id", C.c_int32),
+        ("sample_maps", C.c_int32), ("max_path_length", C.c_int32), ("_pad", C.c_int32),
+        ("layer_norm", C.c_double), ("catchr", C.c_double), ("term_pursuit", C.c_double),
+        ("urgency_reward", C.c_double), ("constraint_window", C.c_double), ("seed", C.c_uint64),
+    ]
+
+
+class PELayout(C.Structure):
+    _fields_ = [
+        ("total_bytes", C.c_size_t), ("pos", C.c_size_t), ("gone", C.c_size_t),
+        ("map_id", C.c_size_t), ("path_len", C.c_size_t), ("rng_counter", C.c_size_t),
+        ("stale", C.c_size_t), ("maps", C.c_size_t), ("lut", C.c_size_t), ("idv", C.c_size_t),
+        ("n_agents", C.c_int32), ("obs_dim", C.c_int32),
+    ]
+
+
 def _declare(lib):
     vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
     lib.madrl_last_error.restype = C.c_char_p
@@ -57,6 +78,19 @@ def _declare(lib):
     lib.madrl_ww_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
     lib.madrl_ww_reset_host.argtypes = [vp, vp, vp]
     lib.madrl_ww_rollout_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
+    lib.madrl_pursuit_state_layout.argtypes = [C.POINTER(PEConfig), C.POINTER(PELayout)]
+    lib.madrl_pursuit_create.argtypes = [C.POINTER(PEConfig), vp, vp, C.POINTER(vp)]
+    lib.madrl_pursuit_destroy.argtypes = [vp]
+    lib.madrl_pursuit_state_ptr.argtypes = [vp]
+    lib.madrl_pursuit_state_ptr.restype = vp
+    lib.madrl_pursuit_seed.argtypes = [vp, u64, vp]
+    lib.madrl_pursuit_set_launch.argtypes = [vp, i32, i32]
+    lib.madrl_pursuit_set_params.argtypes = [vp, C.c_double, C.c_double]
+    lib.madrl_pursuit_reset.argtypes = [vp, vp, vp, vp]
+    lib.madrl_pursuit_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp]
+    lib.madrl_pursuit_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
+    lib.madrl_pursuit_reset_host.argtypes = [vp, vp, vp]
+    lib.madrl_pursuit_rollout_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
 
 
 def lib():

@@ -1,0 +1,616 @@
+// PursuitEvade batched engine: persistent warp-per-env rollout kernel for sm_100a (integer path,
+// bit-exact with the reference).
+//
+// Reference semantics: madrl_environments/pursuit/pursuit_evade.py (pe:LINE) and
+// pursuit/utils/{DiscreteAgent.py (da:), AgentLayer.py (al:), agent_utils.py (au:)}.
+//
+// Design:
+//   * One WARP owns one env for the whole T-step rollout.  Agent coordinates live in registers
+//     (lane q = pursuer q; lane j (+32c) = evader j); the env's three occupancy layers
+//     (pe:244-246 model_state[0:3]) are ONE packed shared-memory word per grid cell
+//     (byte0 = building, byte1 = pursuer count, byte2 = evader count), kept up to date
+//     incrementally with shared-memory atomics as agents move, so a local-observation cell costs
+//     a single LDS.  No block barriers: warps are independent.
+//   * The reference never clears channels 1-2 of its persistent local_obs buffer (pe:119,438), so
+//     out-of-bounds window cells show stale counts.  That buffer is real state: it is kept as
+//     packed u16 (pursuer count | evader count << 8) per window cell in shared memory during the
+//     rollout and in HBM between launches.
+//   * Evader actions: live evader with live-rank r takes draw (ctr + r) of the env's Philox
+//     stream (ct:16 one randint(5) per live evader, in order) -- computed by all lanes at once.
+//   * Observation rows are written cell-major: lane w handles window cell w for all 3 channels
+//     (shared coordinate math), three coalesced stores per 32 cells.
+#include <math.h>
+#include <new>
+
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace madrl {
+
+struct PEParams {
+  int E, env_id_base, Np, Ne, R, off, xs, ys, n_maps, D;
+  int n_catch, surround, reward_global, include_id, sample_maps, max_path_length;
+  int T, mode, auto_reset;
+  int smem_per_warp, cells_pad;   // bytes of shared memory per warp; xs*ys rounded up to 32
+  double constraint_window, catchr, term_pursuit, urgency;
+  float wall_val, one_val;        // float32(1/layer_norm) the two ways the reference gets it
+  uint64_t seed;
+  const uint8_t* maps;            // [n_maps][xs*ys] 1 = building
+  const float* lut;               // [256] float32(count)/float32(layer_norm)
+  const float* idv;               // [Np]  float32(float64(i)/Np)
+  // state records
+  uint8_t* pos;                   // [E][2][Np+Ne]  x row, y row; pursuers then evaders
+  uint64_t* gone;                 // [E] bit j = evader j removed
+  int32_t* map_id;                // [E]
+  int32_t* path_len;              // [E]
+  uint64_t* ctr;                  // [E]
+  uint16_t* stale;                // [E][Np][R*R]  pursuer count | evader count << 8
+  // trajectory tensors
+  const int32_t* actions;         // [T][E][Np]
+  float* obs;                     // [T][E][Np][D]
+  float* rew;                     // [T][E][Np]
+  uint8_t* done;                  // [T][E]
+  int32_t* info;                  // [T][E]  removed
+  const uint8_t* mask;
+};
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// numpy's float64 add.reduce over a contiguous vector: first element + pairwise_sum(rest)
+// (numpy/core/src/umath/loops_utils.h.src DOUBLE_pairwise_sum, n <= 128 path), then / n.
+__device__ __forceinline__ double numpy_mean(const double* a, int n) {
+  const double* b = a + 1;
+  const int m = n - 1;
+  double res;
+  if (m < 8) {
+    res = 0.0;
+    for (int i = 0; i < m; ++i) res += b[i];
+  } else {
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = b[j];
+    int i;
+    for (i = 8; i < m - (m % 8); i += 8)
+      for (int j = 0; j < 8; ++j) r[j] += b[i + j];
+    res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < m; ++i) res += b[i];
+  }
+  return (a[0] + res) / (double)n;
+}
+
+// EPL = evaders per lane (ceil(Ne/32)); CPL = window cells per lane (ceil(R*R/32));
+// RC = compile-time obs_range (0 = runtime p.R).
+template <int EPL, int CPL, int RC>
+__global__ void __launch_bounds__(128, 7) pe_kernel(const __grid_constant__ PEParams p) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  const int warp_global = blockIdx.x * warps_per_block + wib;
+  const int warp_stride = gridDim.x * warps_per_block;
+  const int R = RC > 0 ? RC : p.R, RR = R * R, xs = p.xs, ys = p.ys, ncell = xs * ys;
+  const int Np = p.Np, Ne = p.Ne, Nag = Np + Ne;
+
+  // per-warp shared memory: cell words, then the stale window counts
+  uint32_t* cellw = smem_u32 + (size_t)wib * (p.smem_per_warp / 4);
+  uint16_t* stale = reinterpret_cast<uint16_t*>(cellw + p.cells_pad);
+
+  // per-lane window cell offsets
+  int wdx[CPL], wdy[CPL];
+#pragma unroll
+  for (int it = 0; it < CPL; ++it) {
+    const int w = lane + 32 * it;
+    wdx[it] = w / R - p.off;   // local_obs[i, ch, wx, wy] <-> map cell (x - off + wx, y - off + wy)
+    wdy[it] = w % R - p.off;
+  }
+  const int n_tail = p.include_id ? 1 : 0;
+  const size_t step_stride = (size_t)p.E * Np * p.D;
+
+  for (int e = warp_global; e < p.E; e += warp_stride) {
+    if (p.mode == 1 && p.mask != nullptr && p.mask[e] == 0) continue;
+    const uint32_t env_id = (uint32_t)(p.env_id_base + e);
+    // ---- state -> registers / shared memory --------------------------------------------------
+    const uint8_t* prec = p.pos + (size_t)e * 2 * Nag;
+    int px = 0, py = 0, ex[EPL], ey[EPL];
+    if (lane < Np) { px = prec[lane]; py = prec[Nag + lane]; }
+    unsigned live[EPL];   // warp-uniform: evaders of chunk c still on the map
+    const uint64_t gone0 = p.gone[e];
+#pragma unroll
+    for (int c = 0; c < EPL; ++c) {
+      const int j = lane + 32 * c;
+      ex[c] = ey[c] = 0;
+      if (j < Ne) { ex[c] = prec[Np + j]; ey[c] = prec[Nag + Np + j]; }
+      const unsigned valid = __ballot_sync(FULL_MASK, j < Ne);
+      live[c] = valid & ~(unsigned)(gone0 >> (32 * c));
+    }
+    int map_id = p.map_id[e], ts = p.path_len[e];
+    uint64_t ctr = p.ctr[e];
+    const uint8_t* map = p.maps + (size_t)map_id * ncell;
+    for (int i = lane; i < Np * RR; i += 32) stale[i] = p.stale[(size_t)e * Np * RR + i];
+    bool rebuild = true;   // cell words must be (re)built from map + positions
+
+    float* obs_t = p.obs + (size_t)e * Np * p.D;
+    float* rew_t = p.rew + (size_t)e * Np + lane;
+    const int32_t* act_t = p.actions + (size_t)e * Np + lane;
+    size_t te = (size_t)e;
+    int pass = (p.mode == 1) ? 1 : 0;   // pass 1 = reset(): draws + obs only
+    int act_next = 4;
+    if (p.mode == 0 && lane < Np) act_next = *act_t;
+
+    for (int t = 0; t < p.T; ++t) {
+      int act = act_next;
+      if (p.mode == 0 && t + 1 < p.T && lane < Np) act_next = act_t[(size_t)p.E * Np];
+      bool need_reset;
+      do {
+        int removed = 0;
+        unsigned sur_mask = 0u;      // pursuers that surrounded / tagged a removed evader
+        unsigned caught[EPL];
+        int rcount = 0;              // this pursuer's neighbouring-evader count (pe:374-380)
+#pragma unroll
+        for (int c = 0; c < EPL; ++c) caught[c] = 0u;
+        if (pass) {
+          // ---- reset(): pe:173-203.  All lanes run the same stream (warp-uniform). ------------
+          SeqStream rs;
+          rs.init(p.seed, env_id, 0u, ctr);
+          if (p.sample_maps) map_id = rs.next_range(0, p.n_maps);                    // pe:183
+          map = p.maps + (size_t)map_id * ncell;
+          const double span = 1.0 - p.constraint_window;
+          const double xws = 0.0 + (span - 0.0) * rs.next_unit<double>();             // pe:185
+          const double yws = 0.0 + (span - 0.0) * rs.next_unit<double>();             // pe:186
+          const int xl = (int)((double)xs * xws), xu = (int)((double)xs * (xws + p.constraint_window));
+          const int yl = (int)((double)ys * yws), yu = (int)((double)ys * (yws + p.constraint_window));
+          for (int a = 0; a < Nag; ++a) {                                             // au:31-47
+            int x, y;
+            do {
+              x = rs.next_range(xl, xu);
+              y = rs.next_range(yl, yu);
+            } while (map[x * ys + y] != 0);
+            if (a < Np) { if (lane == a) { px = x; py = y; } }
+            else {
+              const int j = a - Np;
+#pragma unroll
+              for (int c = 0; c < EPL; ++c) if (j == lane + 32 * c) { ex[c] = x; ey[c] = y; }
+            }
+          }
+          ctr = rs.counter;
+          ts = 0;
+#pragma unroll
+          for (int c = 0; c < EPL; ++c) live[c] = __ballot_sync(FULL_MASK, lane + 32 * c < Ne);
+          rebuild = true;
+        }
+        if (rebuild) {   // cell words from scratch: building flag + occupancy counts
+          __syncwarp();
+          for (int i = lane; i < ncell; i += 32) cellw[i] = map[i] ? 1u : 0u;
+          __syncwarp();
+          if (lane < Np) atomicAdd(&cellw[px * ys + py], 1u << 8);
+#pragma unroll
+          for (int c = 0; c < EPL; ++c)
+            if ((live[c] >> lane) & 1u) atomicAdd(&cellw[ex[c] * ys + ey[c]], 1u << 16);
+          __syncwarp();
+          rebuild = false;
+        }
+        if (!pass) {
+          // ---- reward from the PRE-move state: pe:213, 359-381 ---------------------------------
+          if (lane < Np) {
+            const int xm = max(px - 1, 0), xp = min(px + 1, xs - 1);
+            const int ym = max(py - 1, 0), yp = min(py + 1, ys - 1);
+            rcount = (int)((cellw[xm * ys + py] >> 16) & 0xff) + (int)((cellw[xp * ys + py] >> 16) & 0xff) +
+                     (int)((cellw[px * ys + yp] >> 16) & 0xff) + (int)((cellw[px * ys + ym] >> 16) & 0xff);
+          }
+          __syncwarp();
+          // ---- move pursuers: pe:227-235, da:69-97 ---------------------------------------------
+          if (lane < Np) {
+            const int a = act;
+            const int dx = (a == 0) ? -1 : (a == 1 ? 1 : 0), dy = (a == 2) ? 1 : (a == 3 ? -1 : 0);
+            const int nx = px + dx, ny = py + dy, cur = px * ys + py;
+            if ((unsigned)a < 4u && (unsigned)nx < (unsigned)xs && (unsigned)ny < (unsigned)ys &&
+                (cellw[cur] & 0xff) == 0u && (cellw[nx * ys + ny] & 0xff) == 0u) {
+              atomicSub(&cellw[cur], 1u << 8);
+              atomicAdd(&cellw[nx * ys + ny], 1u << 8);
+              px = nx; py = ny;
+            }
+          }
+          // ---- move live evaders, one stream draw each in index order: pe:238-241, ct:16 -------
+          int base_rank = 0;
+#pragma unroll
+          for (int c = 0; c < EPL; ++c) {
+            const bool alive = (live[c] >> lane) & 1u;
+            const int rank = base_rank + __popc(live[c] & lanemask_lt());
+            if (alive) {
+              const int a = u32_to_range(stream_word(p.seed, env_id, 0u, ctr + (uint64_t)rank), 0, 5);
+              const int dx = (a == 0) ? -1 : (a == 1 ? 1 : 0), dy = (a == 2) ? 1 : (a == 3 ? -1 : 0);
+              const int nx = ex[c] + dx, ny = ey[c] + dy, cur = ex[c] * ys + ey[c];
+              if (a < 4 && (unsigned)nx < (unsigned)xs && (unsigned)ny < (unsigned)ys &&
+                  (cellw[cur] & 0xff) == 0u && (cellw[nx * ys + ny] & 0xff) == 0u) {
+                atomicSub(&cellw[cur], 1u << 16);
+                atomicAdd(&cellw[nx * ys + ny], 1u << 16);
+                ex[c] = nx; ey[c] = ny;
+              }
+            }
+            base_rank += __popc(live[c]);
+          }
+          ctr += (uint64_t)base_rank;
+          __syncwarp();
+          // ---- remove_agents: pe:463-521 -----------------------------------------------------------
+#pragma unroll
+          for (int c = 0; c < EPL; ++c) {
+            bool got = false;
+            if ((live[c] >> lane) & 1u) {
+              const int x = ex[c], y = ey[c];
+              if (p.surround) {
+                // neighbours holding >= 1 pursuer (pe:482-485) vs need_to_surround (pe:523-540)
+                int adj = 0, need = 4;
+                if (x == 0 || x == xs - 1) need -= 1;
+                if (y == 0 || y == ys - 1) need -= 1;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                  const int xn = x + (m == 0 ? -1 : (m == 1 ? 1 : 0)), yn = y + (m == 2 ? 1 : (m == 3 ? -1 : 0));
+                  if ((unsigned)xn < (unsigned)xs && (unsigned)yn < (unsigned)ys) {
+                    const uint32_t wv = cellw[xn * ys + yn];
+                    if ((wv >> 8) & 0xff) adj += 1;
+                    // pe:536 skips neighbours with xn <= 0 or yn <= 0: row/column 0 never subtracts
+                    if (xn > 0 && yn > 0 && (wv & 0xff)) need -= 1;
+                  }
+                }
+                got = (adj == need);
+              } else {
+                got = (int)((cellw[x * ys + y] >> 8) & 0xff) >= p.n_catch;            // pe:498
+              }
+            }
+            caught[c] = __ballot_sync(FULL_MASK, got);
+            removed += __popc(caught[c]);
+            // which pursuers take the credit (pe:489-495 / pe:503-506): rare, warp-uniform loop
+            for (unsigned m = caught[c]; m != 0u; m &= m - 1u) {
+              const int j = __ffs(m) - 1;
+              const int cx = __shfl_sync(FULL_MASK, ex[c], j), cy = __shfl_sync(FULL_MASK, ey[c], j);
+              const int ddx = px - cx, ddy = py - cy;
+              const bool credit = p.surround ? (abs(ddx) + abs(ddy) == 1) : (ddx == 0 && ddy == 0);
+              sur_mask |= __ballot_sync(FULL_MASK, lane < Np && credit);
+            }
+          }
+        }
+        // ---- collect_obs: pe:418-461 (flatten): channel-major, then x, then y, then id ----------
+        {
+          float* row = obs_t;
+          uint16_t* st_row = stale;
+          for (int i = 0; i < Np; ++i, row += p.D, st_row += RR) {
+            const int pxi = __shfl_sync(FULL_MASK, px, i), pyi = __shfl_sync(FULL_MASK, py, i);
+#pragma unroll
+            for (int it = 0; it < CPL; ++it) {
+              const int w = lane + 32 * it;
+              if (w < RR) {
+                const int cx = pxi + wdx[it], cy = pyi + wdy[it];
+                // cells beyond 2*off (even obs_range) are never written: treated as out of bounds
+                const bool inb = (unsigned)cx < (unsigned)xs && (unsigned)cy < (unsigned)ys &&
+                                 wdx[it] <= p.off && wdy[it] <= p.off;
+                uint32_t wv = 0u;
+                if (inb) wv = cellw[cx * ys + cy];
+                const uint32_t sv = st_row[w];
+                const uint32_t c1 = inb ? ((wv >> 8) & 0xff) : (sv & 0xff);
+                const uint32_t c2 = inb ? ((wv >> 16) & 0xff) : (sv >> 8);
+                st_row[w] = (uint16_t)(c1 | (c2 << 8));
+                const float v0 = inb ? ((wv & 0xff) ? p.one_val : 0.0f) : p.wall_val;     // pe:433,438
+                const float v1 = c1 == 0u ? 0.0f : (c1 == 1u ? p.one_val : p.lut[c1]);
+                const float v2 = c2 == 0u ? 0.0f : (c2 == 1u ? p.one_val : p.lut[c2]);
+                store_stream(row + w, v0);
+                store_stream(row + RR + w, v1);
+                store_stream(row + 2 * RR + w, v2);
+              }
+            }
+            if (lane < n_tail) store_stream(row + 3 * RR, p.idv[i]);                        // pe:444-445
+          }
+        }
+        need_reset = false;
+        if (!pass) {
+          // ---- rewards (float64 like the reference, narrowed once): pe:254-262 ------------------
+          double r = 0.0;
+          if (lane < Np) {
+            r = p.catchr * (double)rcount;
+            r += p.term_pursuit * (((sur_mask >> lane) & 1u) ? 1.0 : 0.0);
+            r += p.urgency;
+          }
+          if (p.reward_global) {
+            double all[32];
+            for (int q = 0; q < Np; ++q) all[q] = __shfl_sync(FULL_MASK, r, q);
+            r = numpy_mean(all, Np);
+          }
+          if (lane < Np) store_stream(rew_t, (float)r);
+          // ---- the captured evaders leave the map only now (still visible in this obs) -----------
+          int n_live = 0;
+#pragma unroll
+          for (int c = 0; c < EPL; ++c) {
+            if ((caught[c] >> lane) & 1u) atomicSub(&cellw[ex[c] * ys + ey[c]], 1u << 16);
+            live[c] &= ~caught[c];
+            n_live += __popc(live[c]);
+          }
+          __syncwarp();
+          ts += 1;
+          const bool done = (n_live == 0) || (p.max_path_length > 0 && ts >= p.max_path_length);  // pe:384-389
+          if (lane == 0) {
+            p.done[te] = done ? 1 : 0;
+            p.info[te] = removed;
+          }
+          need_reset = done && p.auto_reset;   // VecEnvExecutor.step (vec_env_executor.py:24-27)
+        }
+        pass = need_reset ? 1 : 0;
+      } while (need_reset);
+      obs_t += step_stride;
+      rew_t += (size_t)p.E * Np;
+      act_t += (size_t)p.E * Np;
+      te += (size_t)p.E;
+    }
+    // ---- registers / shared memory -> state records ---------------------------------------------
+    __syncwarp();
+    uint8_t* wrec = p.pos + (size_t)e * 2 * Nag;
+    if (lane < Np) { wrec[lane] = (uint8_t)px; wrec[Nag + lane] = (uint8_t)py; }
+    uint64_t gone = 0;
+#pragma unroll
+    for (int c = 0; c < EPL; ++c) {
+      const int j = lane + 32 * c;
+      if (j < Ne) { wrec[Np + j] = (uint8_t)ex[c]; wrec[Nag + Np + j] = (uint8_t)ey[c]; }
+      const unsigned valid = __ballot_sync(FULL_MASK, j < Ne);
+      gone |= (uint64_t)(valid & ~live[c]) << (32 * c);
+    }
+    for (int i = lane; i < Np * RR; i += 32) p.stale[(size_t)e * Np * RR + i] = stale[i];
+    if (lane == 0) { p.gone[e] = gone; p.map_id[e] = map_id; p.path_len[e] = ts; p.ctr[e] = ctr; }
+    __syncwarp();
+  }
+}
+
+}  // namespace madrl
+
+// =================================================================================================
+// Host side: C ABI
+// =================================================================================================
+using namespace madrl;
+
+struct madrl_pursuit {
+  madrl_pursuit_config cfg;
+  madrl_pursuit_layout lay;
+  char* state;
+  bool owns_state;
+  int device, sms;
+  int warps_per_block, blocks_per_sm;
+  void* stage;
+  size_t stage_bytes;
+};
+
+static int pe_validate(const madrl_pursuit_config* c) {
+  MADRL_REQUIRE(c != nullptr, "config is NULL");
+  MADRL_REQUIRE(c->n_envs > 0, "n_envs must be > 0");
+  MADRL_REQUIRE(c->n_pursuers >= 1 && c->n_pursuers <= 32, "n_pursuers must be in [1,32], got %d", c->n_pursuers);
+  MADRL_REQUIRE(c->n_evaders >= 1 && c->n_evaders <= 64, "n_evaders must be in [1,64], got %d", c->n_evaders);
+  MADRL_REQUIRE(c->xs >= 2 && c->ys >= 2 && c->xs <= 255 && c->ys <= 255 && c->xs * c->ys <= 4096,
+                "map must be between 2x2 and 4096 cells (<= 255 per side)");
+  MADRL_REQUIRE(c->n_maps >= 1, "n_maps must be >= 1");
+  MADRL_REQUIRE(c->obs_range >= 1 && c->obs_range * c->obs_range <= 128, "obs_range must be in [1,11]");
+  MADRL_REQUIRE(c->flatten == 1, "only flatten=True observations are implemented in this round");
+  MADRL_REQUIRE(c->layer_norm != 0.0, "layer_norm must be non-zero");
+  MADRL_REQUIRE(c->constraint_window > 0.0 && c->constraint_window <= 1.0, "constraint_window must be in (0,1]");
+  return MADRL_OK;
+}
+
+extern "C" int madrl_pursuit_state_layout(const madrl_pursuit_config* c, madrl_pursuit_layout* out) {
+  int rc = pe_validate(c);
+  if (rc) return rc;
+  MADRL_REQUIRE(out != nullptr, "layout out is NULL");
+  const size_t E = (size_t)c->n_envs, Nag = (size_t)c->n_pursuers + c->n_evaders;
+  const size_t RR = (size_t)c->obs_range * c->obs_range;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  out->rng_counter = take(8 * E);
+  out->gone = take(8 * E);
+  out->pos = take(2 * Nag * E);
+  out->map_id = take(4 * E);
+  out->path_len = take(4 * E);
+  out->stale = take(2 * (size_t)c->n_pursuers * RR * E);
+  out->maps = take((size_t)c->n_maps * c->xs * c->ys);
+  out->lut = take(4 * 256);
+  out->idv = take(4 * 32);
+  out->total_bytes = off;
+  out->n_agents = (int32_t)Nag;
+  out->obs_dim = (int32_t)(3 * RR + (c->include_id ? 1 : 0));   // pe:108-112
+  return MADRL_OK;
+}
+
+extern "C" int madrl_pursuit_create(const madrl_pursuit_config* c, const int32_t* map_pool_host,
+                                    void* state_dev, madrl_pursuit** out) {
+  MADRL_REQUIRE(out != nullptr && map_pool_host != nullptr, "out / map_pool is NULL");
+  madrl_pursuit_layout lay;
+  int rc = madrl_pursuit_state_layout(c, &lay);
+  if (rc) return rc;
+  madrl_pursuit* h = new (std::nothrow) madrl_pursuit();
+  if (!h) return MADRL_ENOMEM;
+  h->cfg = *c; h->lay = lay; h->stage = nullptr; h->stage_bytes = 0;
+  h->warps_per_block = 0; h->blocks_per_sm = 0;
+  cudaError_t e = cudaGetDevice(&h->device);
+  if (e != cudaSuccess) { set_error("cudaGetDevice: %s", cudaGetErrorString(e)); delete h; return MADRL_ECUDA; }
+  h->sms = sm_count(h->device);
+  if (h->sms <= 0) { delete h; return MADRL_ECUDA; }
+  if (state_dev) { h->state = (char*)state_dev; h->owns_state = false; }
+  else {
+    e = cudaMalloc((void**)&h->state, lay.total_bytes);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu): %s", lay.total_bytes, cudaGetErrorString(e)); delete h; return MADRL_ENOMEM; }
+    h->owns_state = true;
+  }
+  e = cudaMemset(h->state, 0, lay.total_bytes);   // agents start at (0,0), local_obs zeroed (pe:119, au:22)
+  if (e != cudaSuccess) { set_error("cudaMemset: %s", cudaGetErrorString(e)); madrl_pursuit_destroy(h); return MADRL_ECUDA; }
+  // constant tables
+  const size_t ncell = (size_t)c->xs * c->ys, nm = (size_t)c->n_maps;
+  uint8_t* m8 = new (std::nothrow) uint8_t[nm * ncell];
+  if (!m8) { madrl_pursuit_destroy(h); return MADRL_ENOMEM; }
+  for (size_t i = 0; i < nm * ncell; ++i) m8[i] = (map_pool_host[i] == -1) ? 1 : 0;   // da:110-113
+  float lut[256], idv[32];
+  const float lnf = (float)c->layer_norm;
+  for (int k = 0; k < 256; ++k) lut[k] = (float)k / lnf;            // float32 |count| / layer_norm (pe:438)
+  for (int i = 0; i < 32; ++i) idv[i] = (float)((double)i / (double)c->n_pursuers);   // pe:445
+  e = cudaMemcpy(h->state + lay.maps, m8, nm * ncell, cudaMemcpyHostToDevice);
+  delete[] m8;
+  if (e == cudaSuccess) e = cudaMemcpy(h->state + lay.lut, lut, sizeof(lut), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->state + lay.idv, idv, sizeof(idv), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { set_error("cudaMemcpy(tables): %s", cudaGetErrorString(e)); madrl_pursuit_destroy(h); return MADRL_ECUDA; }
+  *out = h;
+  return MADRL_OK;
+}
+
+extern "C" int madrl_pursuit_destroy(madrl_pursuit* h) {
+  if (!h) return MADRL_OK;
+  if (h->owns_state && h->state) cudaFree(h->state);
+  if (h->stage) cudaFree(h->stage);
+  delete h;
+  return MADRL_OK;
+}
+
+extern "C" void* madrl_pursuit_state_ptr(madrl_pursuit* h) { return h ? h->state : nullptr; }
+
+extern "C" int madrl_pursuit_seed(madrl_pursuit* h, uint64_t seed, void* stream) {
+  MADRL_REQUIRE(h != nullptr, "handle is NULL");
+  h->cfg.seed = seed;
+  MADRL_CUDA_CHECK(cudaMemsetAsync(h->state + h->lay.rng_counter, 0, 8 * (size_t)h->cfg.n_envs, (cudaStream_t)stream));
+  return MADRL_OK;
+}
+
+extern "C" int madrl_pursuit_set_launch(madrl_pursuit* h, int warps_per_block, int blocks_per_sm) {
+  MADRL_REQUIRE(h != nullptr, "handle is NULL");
+  MADRL_REQUIRE(warps_per_block >= 0 && warps_per_block <= 4, "warps_per_block must be in [0,4]");
+  MADRL_REQUIRE(blocks_per_sm >= 0 && blocks_per_sm <= 32, "blocks_per_sm must be in [0,32]");
+  h->warps_per_block = warps_per_block; h->blocks_per_sm = blocks_per_sm;
+  return MADRL_OK;
+}
+
+extern "C" int madrl_pursuit_set_params(madrl_pursuit* h, double catchr, double constraint_window) {
+  MADRL_REQUIRE(h != nullptr, "handle is NULL");
+  MADRL_REQUIRE(constraint_window > 0.0 && constraint_window <= 1.0, "constraint_window must be in (0,1]");
+  h->cfg.catchr = catchr; h->cfg.constraint_window = constraint_window;
+  return MADRL_OK;
+}
+
+template <int EPL, int CPL, int RC>
+static int pe_launch_inst(madrl_pursuit* h, PEParams& p, cudaStream_t stream) {
+  const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 4;
+  const size_t smem = (size_t)wpb * p.smem_per_warp;
+  MADRL_REQUIRE(smem <= 200 * 1024, "map too large for shared memory (%zu B per block)", smem);
+  if (smem > 48 * 1024)
+    MADRL_CUDA_CHECK(cudaFuncSetAttribute(pe_kernel<EPL, CPL, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int resident = 0;
+  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pe_kernel<EPL, CPL, RC>, wpb * 32, smem));
+  if (resident < 1) resident = 1;
+  if (h->blocks_per_sm > 0 && h->blocks_per_sm < resident) resident = h->blocks_per_sm;
+  int grid = (p.E + wpb - 1) / wpb;
+  if (grid > h->sms * resident) grid = h->sms * resident;
+  pe_kernel<EPL, CPL, RC><<<grid, wpb * 32, smem, stream>>>(p);
+  g_launches.fetch_add(1);
+  MADRL_CUDA_CHECK(cudaGetLastError());
+  return MADRL_OK;
+}
+
+static int pe_launch(madrl_pursuit* h, int mode, int T, const int32_t* actions, float* obs, float* rew,
+                     uint8_t* done, int32_t* info, const uint8_t* mask, int auto_reset, cudaStream_t stream) {
+  const madrl_pursuit_config& c = h->cfg;
+  PEParams p;
+  p.E = c.n_envs; p.env_id_base = c.env_id_base; p.Np = c.n_pursuers; p.Ne = c.n_evaders;
+  p.R = c.obs_range; p.off = (int)((c.obs_range - 1) / 2);   // pe:65
+  p.xs = c.xs; p.ys = c.ys; p.n_maps = c.n_maps; p.D = h->lay.obs_dim;
+  p.n_catch = c.n_catch; p.surround = c.surround; p.reward_global = c.reward_global;
+  p.include_id = c.include_id; p.sample_maps = c.sample_maps; p.max_path_length = c.max_path_length;
+  p.T = T; p.mode = mode; p.auto_reset = auto_reset;
+  const int ncell = c.xs * c.ys, RR = c.obs_range * c.obs_range;
+  p.cells_pad = (ncell + 31) / 32 * 32;
+  p.smem_per_warp = (int)align_up((size_t)p.cells_pad * 4 + (size_t)c.n_pursuers * RR * 2, 16);
+  p.constraint_window = c.constraint_window; p.catchr = c.catchr; p.term_pursuit = c.term_pursuit;
+  p.urgency = c.urgency_reward;
+  p.wall_val = (float)(1.0 / c.layer_norm);           // local_obs[i][0].fill(1.0 / layer_norm): f64 -> f32
+  p.one_val = 1.0f / (float)c.layer_norm;             // float32 |+-1| / layer_norm
+  p.seed = c.seed;
+  char* st = h->state;
+  p.maps = (const uint8_t*)(st + h->lay.maps); p.lut = (const float*)(st + h->lay.lut);
+  p.idv = (const float*)(st + h->lay.idv);
+  p.pos = (uint8_t*)(st + h->lay.pos); p.gone = (uint64_t*)(st + h->lay.gone);
+  p.map_id = (int32_t*)(st + h->lay.map_id); p.path_len = (int32_t*)(st + h->lay.path_len);
+  p.ctr = (uint64_t*)(st + h->lay.rng_counter); p.stale = (uint16_t*)(st + h->lay.stale);
+  p.actions = actions; p.obs = obs; p.rew = rew; p.done = done; p.info = info; p.mask = mask;
+  const int epl = (p.Ne + 31) / 32, cpl = (RR + 31) / 32;
+#define MADRL_PE_CASE(EP, CP, RC_) return pe_launch_inst<EP, CP, RC_>(h, p, stream)
+  if (p.R == 7) { if (epl == 1) MADRL_PE_CASE(1, 2, 7); MADRL_PE_CASE(2, 2, 7); }
+  if (cpl == 1) { if (epl == 1) MADRL_PE_CASE(1, 1, 0); MADRL_PE_CASE(2, 1, 0); }
+  if (cpl == 2) { if (epl == 1) MADRL_PE_CASE(1, 2, 0); MADRL_PE_CASE(2, 2, 0); }
+  if (epl == 1) MADRL_PE_CASE(1, 4, 0);
+  MADRL_PE_CASE(2, 4, 0);
+#undef MADRL_PE_CASE
+}
+
+extern "C" int madrl_pursuit_reset(madrl_pursuit* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+  MADRL_REQUIRE(h != nullptr && obs_dev != nullptr, "handle/obs is NULL");
+  return pe_launch(h, 1, 1, nullptr, obs_dev, nullptr, nullptr, nullptr, mask_dev, 0, (cudaStream_t)stream);
+}
+
+extern "C" int madrl_pursuit_rollout(madrl_pursuit* h, int T, const int32_t* actions_dev, float* obs_dev,
+                                     float* rew_dev, uint8_t* done_dev, int32_t* info_dev,
+                                     int auto_reset, void* stream) {
+  MADRL_REQUIRE(h != nullptr, "handle is NULL");
+  MADRL_REQUIRE(T >= 1, "T must be >= 1");
+  MADRL_REQUIRE(actions_dev && obs_dev && rew_dev && done_dev && info_dev, "NULL trajectory buffer");
+  return pe_launch(h, 0, T, actions_dev, obs_dev, rew_dev, done_dev, info_dev, nullptr, auto_reset, (cudaStream_t)stream);
+}
+
+extern "C" int madrl_pursuit_step(madrl_pursuit* h, const int32_t* actions_dev, float* obs_dev, float* rew_dev,
+                                  uint8_t* done_dev, int32_t* info_dev, int auto_reset, void* stream) {
+  return madrl_pursuit_rollout(h, 1, actions_dev, obs_dev, rew_dev, done_dev, info_dev, auto_reset, stream);
+}
+
+static int pe_stage(madrl_pursuit* h, size_t bytes) {
+  if (h->stage_bytes >= bytes) return MADRL_OK;
+  if (h->stage) cudaFree(h->stage);
+  h->stage = nullptr; h->stage_bytes = 0;
+  cudaError_t e = cudaMalloc(&h->stage, bytes);
+  if (e != cudaSuccess) { set_error("cudaMalloc(stage %zu): %s", bytes, cudaGetErrorString(e)); return MADRL_ENOMEM; }
+  h->stage_bytes = bytes;
+  return MADRL_OK;
+}
+
+extern "C" int madrl_pursuit_reset_host(madrl_pursuit* h, const uint8_t* mask_host, float* obs_host) {
+  MADRL_REQUIRE(h != nullptr && obs_host != nullptr, "handle/obs is NULL");
+  const size_t E = h->cfg.n_envs;
+  const size_t obs_b = E * h->cfg.n_pursuers * h->lay.obs_dim * 4, mask_off = align_up(obs_b, 256);
+  int rc = pe_stage(h, mask_off + E);
+  if (rc) return rc;
+  char* st = (char*)h->stage;
+  uint8_t* mask_dev = nullptr;
+  if (mask_host) {
+    mask_dev = (uint8_t*)(st + mask_off);
+    MADRL_CUDA_CHECK(cudaMemcpyAsync(mask_dev, mask_host, E, cudaMemcpyHostToDevice, 0));
+    MADRL_CUDA_CHECK(cudaMemcpyAsync(st, obs_host, obs_b, cudaMemcpyHostToDevice, 0));
+  }
+  rc = madrl_pursuit_reset(h, mask_dev, (float*)st, nullptr);
+  if (rc) return rc;
+  MADRL_CUDA_CHECK(cudaMemcpyAsync(obs_host, st, obs_b, cudaMemcpyDeviceToHost, 0));
+  MADRL_CUDA_CHECK(cudaStreamSynchronize(0));
+  return MADRL_OK;
+}
+
+extern "C" int madrl_pursuit_rollout_host(madrl_pursuit* h, int T, const int32_t* actions_host, float* obs_host,
+                                          float* rew_host, uint8_t* done_host, int32_t* info_host, int auto_reset) {
+  MADRL_REQUIRE(h != nullptr, "handle is NULL");
+  MADRL_REQUIRE(T >= 1, "T must be >= 1");
+  MADRL_REQUIRE(actions_host && obs_host && rew_host && done_host && info_host, "NULL trajectory buffer");
+  const size_t E = h->cfg.n_envs, Np = h->cfg.n_pursuers, TT = (size_t)T;
+  const size_t act_b = TT * E * Np * 4, obs_b = TT * E * Np * h->lay.obs_dim * 4, rew_b = TT * E * Np * 4;
+  const size_t done_b = TT * E, info_b = TT * E * 4;
+  const size_t o_obs = align_up(act_b, 256), o_rew = align_up(o_obs + obs_b, 256);
+  const size_t o_done = align_up(o_rew + rew_b, 256), o_info = align_up(o_done + done_b, 256);
+  int rc = pe_stage(h, o_info + info_b);
+  if (rc) return rc;
+  char* st = (char*)h->stage;
+  MADRL_CUDA_CHECK(cudaMemcpyAsync(st, actions_host, act_b, cudaMemcpyHostToDevice, 0));
+  rc = madrl_pursuit_rollout(h, T, (const int32_t*)st, (float*)(st + o_obs), (float*)(st + o_rew),
+                             (uint8_t*)(st + o_done), (int32_t*)(st + o_info), auto_reset, nullptr);
+  if (rc) return rc;
+  MADRL_CUDA_CHECK(cudaMemcpyAsync(obs_host, st + o_obs, obs_b, cudaMemcpyDeviceToHost, 0));
+  MADRL_CUDA_CHECK(cudaMemcpyAsync(rew_host, st + o_rew, rew_b, cudaMemcpyDeviceToHost, 0));
+  MADRL_CUDA_CHECK(cudaMemcpyAsync(done_host, st + o_done, done_b, cudaMemcpyDeviceToHost, 0));
+  MADRL_CUDA_CHECK(cudaMemcpyAsync(info_host, st + o_info, info_b, cudaMemcpyDeviceToHost, 0));
+  MADRL_CUDA_CHECK(cudaStreamSynchronize(0));
+  return MADRL_OK;
+}

@@ -57,10 +57,69 @@ def gen_waterworld(MAWaterWorld):
         print(name, "catches", np.array(info).sum(0), "draws", env.np_random.counter)
 
 
+PE_C3 = dict(n_evaders=30, n_pursuers=8, obs_range=7, surround=True, n_catch=2, flatten=True,
+             reward_mech='local', catchr=0.1, term_pursuit=5.0, sample_maps=True, include_id=True)
+PE_CASES = {
+    # name: (map source, ctor kwargs, seed, env_id, T, resets every)
+    "pe_c3": ("pool16", PE_C3, 21, 5, 160, 0),
+    "pe_c3_global": ("pool16", dict(PE_C3, reward_mech='global', urgency_reward=-0.1), 22, 70000, 120, 50),
+    "pe_ncatch": ("pool16", dict(PE_C3, surround=False, n_evaders=20, n_pursuers=12, obs_range=5), 23, 1, 160, 0),
+    "pe_window": ("pool16", dict(PE_C3, constraint_window=0.5, n_evaders=6, n_pursuers=10, obs_range=9,
+                                 include_id=False), 24, 2, 200, 70),
+    "pe_small": ("small5", dict(n_evaders=2, n_pursuers=4, obs_range=3, surround=True, reward_mech='local',
+                                catchr=0.1, sample_maps=False), 25, 3, 1500, 0),
+    "pe_crowd": ("small5", dict(n_evaders=4, n_pursuers=10, obs_range=3, surround=True, reward_mech='local',
+                                catchr=0.1, term_pursuit=5.0, sample_maps=False), 27, 6, 600, 0),
+    "pe_even_range": ("small5", dict(n_evaders=3, n_pursuers=3, obs_range=4, surround=False, n_catch=1,
+                                     reward_mech='global'), 26, 4, 200, 0),
+}
+
+
+def small_map():
+    m = np.zeros((1, 5, 5), dtype=np.int32)
+    m[0, 2, 2] = -1
+    return m
+
+
+def gen_pursuit():
+    from oracle.refshim import make_reference_pursuit, REFERENCE_ROOT
+    pool16 = np.load(os.path.join(REFERENCE_ROOT, "maps", "map_pool16.npy"))
+    # the map pool is an INPUT fixture of BASELINE.json configs 1 and 3 (reference file
+    # maps/map_pool16.npy, int32 (10,16,16), -1 = building); kept at the same relative path
+    os.makedirs(os.path.join(ROOT, "maps"), exist_ok=True)
+    np.save(os.path.join(ROOT, "maps", "map_pool16.npy"), pool16)
+    for name, (msrc, kw, seed, env_id, T, every) in PE_CASES.items():
+        maps = pool16 if msrc == "pool16" else small_map()
+        stream = Stream(seed, env_id)
+        env = make_reference_pursuit(maps, stream, **kw)
+        Np = kw['n_pursuers']
+        arng = np.random.RandomState(seed)
+        actions = arng.randint(0, 5, size=(T, Np)).astype(np.int32)
+        obs0 = np.array(env.reset())
+        obs, rew, done, removed, reset_at, reset_obs = [], [], [], [], [], []
+        for t in range(T):
+            o, r, d, i = env.step(actions[t])
+            obs.append(np.array(o)); rew.append(np.asarray(r, dtype=np.float64)); done.append(d)
+            removed.append(i['removed'])
+            if d or (every and t % every == every - 1):
+                reset_at.append(t)
+                reset_obs.append(np.array(env.reset()))
+        np.savez_compressed(
+            os.path.join(GOLDEN, name + ".npz"), config=json.dumps(kw), maps=msrc, seed=seed,
+            env_id=env_id, actions=actions, obs0=obs0, obs=np.array(obs), rew=np.array(rew),
+            done=np.array(done), removed=np.array(removed, dtype=np.int32),
+            reset_at=np.array(reset_at, dtype=np.int32),
+            reset_obs=np.array(reset_obs) if reset_obs else np.zeros((0,) + obs0.shape),
+            counter=stream.counter)
+        print(name, "removed", int(np.sum(removed)), "dones", int(np.sum(done)), "resets", len(reset_at),
+              "draws", stream.counter)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     MAWaterWorld, PursuitEvade, ContinuousHostageWorld = load_reference()
     gen_waterworld(MAWaterWorld)
+    gen_pursuit()
 
 
 if __name__ == "__main__":

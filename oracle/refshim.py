@@ -137,3 +137,30 @@ def load_reference():
     from madrl_environments.pursuit.pursuit_evade import PursuitEvade
     from madrl_environments.hostage import ContinuousHostageWorld
     return MAWaterWorld, PursuitEvade, ContinuousHostageWorld
+
+
+class _NumpyProxy(object):
+    """Stands in for the ``np`` global of a reference module: ``.random`` is the injected stream,
+    everything else is the real numpy."""
+
+    def __init__(self, stream):
+        self.random = stream
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+
+def make_reference_pursuit(map_pool, stream, **kwargs):
+    """Real ``PursuitEvade`` whose every random draw (``np.random.randint/uniform`` in
+    pursuit_evade.py:183-186 and utils/agent_utils.py:39-45, evader ``controller.act`` at
+    pursuit_evade.py:240) comes from ``stream``.  The module-level ``np`` of the two reference
+    modules is swapped for a proxy while the returned env is in use (single env at a time)."""
+    install()
+    from madrl_environments.pursuit import pursuit_evade as pe_mod
+    from madrl_environments.pursuit.utils import agent_utils as au_mod
+    from oracle.philox import StreamController
+    proxy = _NumpyProxy(stream)
+    pe_mod.np = proxy
+    au_mod.np = proxy
+    env = pe_mod.PursuitEvade(map_pool, evader_controller=StreamController(5, stream), **kwargs)
+    return env
