@@ -60,25 +60,26 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   return m;
 }
 
-// numpy's float64 add.reduce over a contiguous vector: first element + pairwise_sum(rest)
-// (numpy/core/src/umath/loops_utils.h.src DOUBLE_pairwise_sum, n <= 128 path), then / n.
+// float64 `ndarray.mean()` exactly as NumPy (>= 1.22, checked against 2.3.5) computes it for a
+// contiguous vector of n <= 128 elements: DOUBLE_pairwise_sum over the WHOLE vector
+// (numpy/_core/src/umath/loops_utils.h.src: n < 8 -> sequential from -0.0; else 8 interleaved
+// accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail), divided by n.
 __device__ __forceinline__ double numpy_mean(const double* a, int n) {
-  const double* b = a + 1;
-  const int m = n - 1;
   double res;
-  if (m < 8) {
-    res = 0.0;
-    for (int i = 0; i < m; ++i) res += b[i];
+  if (n < 8) {
+    res = -0.0;
+    for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
   } else {
     double r[8];
-    for (int j = 0; j < 8; ++j) r[j] = b[j];
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
     int i;
-    for (i = 8; i < m - (m % 8); i += 8)
-      for (int j = 0; j < 8; ++j) r[j] += b[i + j];
-    res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-    for (; i < m; ++i) res += b[i];
+    for (i = 8; i < n - (n % 8); i += 8)
+      for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+    res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                    __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
   }
-  return (a[0] + res) / (double)n;
+  return __ddiv_rn(res, (double)n);
 }
 
 // EPL = evaders per lane (ceil(Ne/32)); CPL = window cells per lane (ceil(R*R/32));
@@ -307,9 +308,11 @@ __global__ void __launch_bounds__(128, 7) pe_kernel(const __grid_constant__ PEPa
           // ---- rewards (float64 like the reference, narrowed once): pe:254-262 ------------------
           double r = 0.0;
           if (lane < Np) {
-            r = p.catchr * (double)rcount;
-            r += p.term_pursuit * (((sur_mask >> lane) & 1u) ? 1.0 : 0.0);
-            r += p.urgency;
+            // explicit round-to-nearest ops: no FMA contraction, so every intermediate rounds
+            // exactly like NumPy's float64 arithmetic
+            r = __dmul_rn(p.catchr, (double)rcount);
+            r = __dadd_rn(r, __dmul_rn(p.term_pursuit, ((sur_mask >> lane) & 1u) ? 1.0 : 0.0));
+            r = __dadd_rn(r, p.urgency);
           }
           if (p.reward_global) {
             double all[32];
