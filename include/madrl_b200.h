@@ -169,6 +169,52 @@ int madrl_pursuit_rollout_host(madrl_pursuit* h, int T, const int32_t* actions_h
                                float* rew_host, uint8_t* done_host, int32_t* info_host,
                                int auto_reset);
 
+/* ------------------------------------------------------------------ ContinuousHostageWorld -- */
+typedef struct madrl_hostage_config {
+  int32_t n_envs, env_id_base;
+  int32_t n_good, n_hostages, n_bad, n_coop_save, n_coop_avoid, n_sensors;   /* hostage.py:75-76 */
+  int32_t reward_global, addid;
+  int32_t random_key;       /* key_loc is None: drawn at the first reset, then kept (hostage.py:148) */
+  int32_t timestep_limit, max_path_length, fp64;
+  double radius, key_x, key_y, bad_speed, sensor_range, action_scale, save_reward, hit_reward,
+      encounter_reward, not_saved_reward, bomb_reward, bomb_radius, key_radius, control_penalty;
+  uint64_t seed;
+} madrl_hostage_config;
+
+typedef struct madrl_hostage_layout {
+  size_t total_bytes;
+  size_t objs;         /* real  [E][4][n_obj] rows x, y, vx, vy; rescuers, criminals, hostages   */
+  size_t fixed;        /* real  [E][4] key x, key y, bomb x, bomb y                              */
+  size_t saved;        /* uint8 [E][n_hostages] curr_host_saved_mask                             */
+  size_t flags;        /* int32 [E] bit0 gate open, bit1 bombed, bit2 key location drawn         */
+  size_t timestep, path_len;   /* int32 [E]                                                      */
+  size_t rng_counter;  /* uint64 [E]                                                             */
+  size_t sensors;      /* real [2][n_sensors]                                                    */
+  int32_t n_obj, obs_dim, real_bytes, _pad;
+} madrl_hostage_layout;
+
+typedef struct madrl_hostage madrl_hostage;
+
+int madrl_hostage_state_layout(const madrl_hostage_config* cfg, madrl_hostage_layout* out);
+int madrl_hostage_create(const madrl_hostage_config* cfg, void* state_dev, madrl_hostage** out);
+int madrl_hostage_destroy(madrl_hostage* h);
+void* madrl_hostage_state_ptr(madrl_hostage* h);
+int madrl_hostage_seed(madrl_hostage* h, uint64_t seed, void* stream);
+int madrl_hostage_set_launch(madrl_hostage* h, int warps_per_block, int blocks_per_sm);
+/* obs_dev real [E][n_good][obs_dim] */
+int madrl_hostage_reset(madrl_hostage* h, const uint8_t* mask_dev, void* obs_dev, void* stream);
+/* actions_dev real [T][E][n_good][2]; obs_dev real [T][E][n_good][obs_dim]; rew_dev real
+ * [T][E][n_good]; done_dev uint8 [T][E]; info_dev int32 [T][E][2] = (ho_saved, cr_encs). */
+int madrl_hostage_rollout(madrl_hostage* h, int T, const void* actions_dev, void* obs_dev,
+                          void* rew_dev, uint8_t* done_dev, int32_t* info_dev, int auto_reset,
+                          void* stream);
+int madrl_hostage_step(madrl_hostage* h, const void* actions_dev, void* obs_dev, void* rew_dev,
+                       uint8_t* done_dev, int32_t* info_dev, int auto_reset, void* stream);
+int madrl_hostage_reset_host(madrl_hostage* h, const uint8_t* mask_host, void* obs_host);
+int madrl_hostage_rollout_host(madrl_hostage* h, int T, const void* actions_host, void* obs_host,
+                               void* rew_host, uint8_t* done_host, int32_t* info_host,
+                               int auto_reset);
+
 #ifdef __cplusplus
 }
 #endif

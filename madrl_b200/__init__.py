@@ -11,9 +11,10 @@ from .core import Agent, AbstractMAEnv, EzPickle  # noqa: F401
 from .spaces import Box, Discrete  # noqa: F401
 from .waterworld import BatchedMAWaterWorld, MAWaterWorld, Archea  # noqa: F401
 from .pursuit import BatchedPursuitEvade, PursuitEvade, DiscreteAgent  # noqa: F401
+from .hostage import BatchedHostageWorld, ContinuousHostageWorld, CircAgent  # noqa: F401
 
 __all__ = [
     "EngineError", "launch_count", "Agent", "AbstractMAEnv", "EzPickle", "Box", "Discrete",
     "BatchedMAWaterWorld", "MAWaterWorld", "Archea", "BatchedPursuitEvade", "PursuitEvade",
-    "DiscreteAgent",
+    "DiscreteAgent", "BatchedHostageWorld", "ContinuousHostageWorld", "CircAgent",
 ]

@@ -61,6 +61,30 @@ class PELayout(C.Structure):
     ]
 
 
+class HWConfig(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32), ("env_id_base", C.c_int32), ("n_good", C.c_int32),
+        ("n_hostages", C.c_int32), ("n_bad", C.c_int32), ("n_coop_save", C.c_int32),
+        ("n_coop_avoid", C.c_int32), ("n_sensors", C.c_int32), ("reward_global", C.c_int32),
+        ("addid", C.c_int32), ("random_key", C.c_int32), ("timestep_limit", C.c_int32),
+        ("max_path_length", C.c_int32), ("fp64", C.c_int32),
+        ("radius", C.c_double), ("key_x", C.c_double), ("key_y", C.c_double),
+        ("bad_speed", C.c_double), ("sensor_range", C.c_double), ("action_scale", C.c_double),
+        ("save_reward", C.c_double), ("hit_reward", C.c_double), ("encounter_reward", C.c_double),
+        ("not_saved_reward", C.c_double), ("bomb_reward", C.c_double), ("bomb_radius", C.c_double),
+        ("key_radius", C.c_double), ("control_penalty", C.c_double), ("seed", C.c_uint64),
+    ]
+
+
+class HWLayout(C.Structure):
+    _fields_ = [
+        ("total_bytes", C.c_size_t), ("objs", C.c_size_t), ("fixed", C.c_size_t),
+        ("saved", C.c_size_t), ("flags", C.c_size_t), ("timestep", C.c_size_t),
+        ("path_len", C.c_size_t), ("rng_counter", C.c_size_t), ("sensors", C.c_size_t),
+        ("n_obj", C.c_int32), ("obs_dim", C.c_int32), ("real_bytes", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
 def _declare(lib):
     vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
     lib.madrl_last_error.restype = C.c_char_p
@@ -78,6 +102,18 @@ def _declare(lib):
     lib.madrl_ww_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
     lib.madrl_ww_reset_host.argtypes = [vp, vp, vp]
     lib.madrl_ww_rollout_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
+    lib.madrl_hostage_state_layout.argtypes = [C.POINTER(HWConfig), C.POINTER(HWLayout)]
+    lib.madrl_hostage_create.argtypes = [C.POINTER(HWConfig), vp, C.POINTER(vp)]
+    lib.madrl_hostage_destroy.argtypes = [vp]
+    lib.madrl_hostage_state_ptr.argtypes = [vp]
+    lib.madrl_hostage_state_ptr.restype = vp
+    lib.madrl_hostage_seed.argtypes = [vp, u64, vp]
+    lib.madrl_hostage_set_launch.argtypes = [vp, i32, i32]
+    lib.madrl_hostage_reset.argtypes = [vp, vp, vp, vp]
+    lib.madrl_hostage_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp]
+    lib.madrl_hostage_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
+    lib.madrl_hostage_reset_host.argtypes = [vp, vp, vp]
+    lib.madrl_hostage_rollout_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
     lib.madrl_pursuit_state_layout.argtypes = [C.POINTER(PEConfig), C.POINTER(PELayout)]
     lib.madrl_pursuit_create.argtypes = [C.POINTER(PEConfig), vp, vp, C.POINTER(vp)]
     lib.madrl_pursuit_destroy.argtypes = [vp]

@@ -31,16 +31,33 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ into one shared library.  Returns the .so path."""
+    """Compile every .cu under csrc/ (in parallel) and link one shared library.  Returns its path."""
     if not force and not _stale():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + cflags + ["-c", "-o", obj, src]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return obj, cmd, res
+
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        results = list(pool.map(compile_one, sources()))
+    for obj, cmd, res in results:
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed (%d): %s" % (res.returncode, " ".join(cmd)))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [r[0] for r in results]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed (%d): %s" % (res.returncode, " ".join(cmd)))
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("nvcc link failed (%d): %s" % (res.returncode, " ".join(cmd)))
     return LIB
 
 

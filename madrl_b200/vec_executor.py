@@ -73,3 +73,15 @@ class PursuitVecExecutor(_BatchedVecExecutor):
 
     def _actions(self, action_n):
         return torch.as_tensor(np.asarray(action_n, dtype=np.int32).reshape(self._n, self._proto.n_pursuers))
+
+
+class HostageVecExecutor(_BatchedVecExecutor):
+    def __init__(self, proto_env, n_envs, max_path_length):
+        from .hostage import BatchedHostageWorld
+        eng = BatchedHostageWorld(n_envs, seed=proto_env._seed_value, max_path_length=max_path_length,
+                                  **proto_env._ctor_params(), **proto_env._engine_kwargs)
+        super().__init__(proto_env, eng, n_envs, max_path_length)
+
+    def _actions(self, action_n):
+        a = np.asarray(action_n, dtype=np.float64).reshape(self._n, self._proto.n_good, 2)
+        return torch.as_tensor(a)

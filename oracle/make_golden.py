@@ -115,11 +115,52 @@ def gen_pursuit():
               "draws", stream.counter)
 
 
+HW_CASES = {
+    # name: (positional args, kwargs, seed, env_id, T, action_std)
+    "hw_c5": ((10, 16, 16, 4, 2), {}, 31, 8, 120, 0.5),
+    "hw_c5_local": ((10, 16, 16, 4, 2), dict(reward_mech='local'), 32, 9000, 150, 2.0),
+    "hw_dense": ((3, 10, 5, 1, 2), dict(radius=0.05, sensor_range=0.35, key_radius=0.06, reward_mech='local',
+                                        addid=False), 33, 1, 400, 3.0),
+    "hw_k12": ((4, 6, 8, 2, 1), dict(radius=0.04, n_sensors=12, key_radius=0.05, bomb_radius=0.02,
+                                     key_loc=[[0.93, 0.97]]), 34, 2, 400, 3.0),
+}
+
+
+def gen_hostage(ContinuousHostageWorld):
+    for name, (args, kw, seed, env_id, T, std) in HW_CASES.items():
+        kw2 = dict(kw)
+        if 'key_loc' in kw2:
+            kw2['key_loc'] = np.array(kw2['key_loc'])
+        env = ContinuousHostageWorld(*args, **kw2)
+        env.np_random = Stream(seed, env_id)
+        Nr = args[0]
+        obs0 = np.array(env.reset())
+        arng = np.random.RandomState(seed)
+        actions = (arng.randn(T, Nr, 2) * std).astype(np.float32).astype(np.float64)
+        obs, rew, done, info, reset_at, reset_obs = [], [], [], [], [], []
+        for t in range(T):
+            o, r, d, i = env.step(actions[t])
+            obs.append(np.array(o)); rew.append(np.array(r)); done.append(d)
+            info.append([i['ho_saved'], i['cr_encs']])
+            if d:
+                reset_at.append(t)
+                reset_obs.append(np.array(env.reset()))
+        np.savez_compressed(
+            os.path.join(GOLDEN, name + ".npz"), args=np.array(args), config=json.dumps(kw), seed=seed,
+            env_id=env_id, actions=actions, obs0=obs0, obs=np.array(obs), rew=np.array(rew),
+            done=np.array(done), info=np.array(info, dtype=np.int32),
+            reset_at=np.array(reset_at, dtype=np.int32),
+            reset_obs=np.array(reset_obs) if reset_obs else np.zeros((0,) + obs0.shape),
+            counter=env.np_random.counter)
+        print(name, "saved/encs", np.array(info).sum(0), "dones", int(np.sum(done)), "draws", env.np_random.counter)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     MAWaterWorld, PursuitEvade, ContinuousHostageWorld = load_reference()
     gen_waterworld(MAWaterWorld)
     gen_pursuit()
+    gen_hostage(ContinuousHostageWorld)
 
 
 if __name__ == "__main__":
