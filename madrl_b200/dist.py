@@ -1,0 +1,79 @@
+"""Env-axis sharding across the GPUs of one box.
+
+Env instances are independent, so the batch shards trivially: rank r owns the contiguous global
+env range ``shard_range(E, r, W)`` and builds its engine with ``env_id_base = lo`` -- the RNG key
+is (seed, GLOBAL env id), so a sharded batch reproduces the unsharded one bit for bit.  There is
+no collective inside the step loop; once per rollout the trajectory tensors are exchanged with
+ONE ``all_gather`` (or gather-to-rank) per tensor over NCCL/NVLink (``gloo`` on CPU in the tests).
+This is the B200 counterpart of the reference's pickled-path return from sampler workers
+(rllab/rllab/sampler/stateful_pool.py:102-157, rltools/rltools/samplers/parallel.py:214-222).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def world_info():
+    """(rank, world_size, local_rank) from torchrun's environment (1 process = 1 GPU)."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def shard_range(n_envs_global, rank, world):
+    """Contiguous, balanced partition of [0, n_envs_global): returns (lo, hi) for `rank`."""
+    lo = (n_envs_global * rank) // world
+    hi = (n_envs_global * (rank + 1)) // world
+    return lo, hi
+
+
+def make_sharded(engine_cls, n_envs_global, *args, rank=None, world=None, **kwargs):
+    """Build this rank's shard of a Batched* engine (env ids [lo, hi) of the global batch)."""
+    r, w, _ = world_info()
+    rank = r if rank is None else rank
+    world = w if world is None else world
+    lo, hi = shard_range(n_envs_global, rank, world)
+    if hi <= lo:
+        raise ValueError("rank %d of %d owns no envs of a %d-env batch" % (rank, world, n_envs_global))
+    eng = engine_cls(hi - lo, *args, env_id_base=kwargs.pop("env_id_base", 0) + lo, **kwargs)
+    eng.shard = (lo, hi, n_envs_global)
+    return eng
+
+
+def gather_trajectories(tensors, env_dim=1, group=None, dst=None, equal_shards=True):
+    """All-gather (or gather to `dst`) per-rank trajectory tensors along the env axis.
+
+    `tensors`: tuple of tensors shaped [T, E_local, ...] (env_dim=1) or [E_local, ...] (env_dim=0).
+    Returns a tuple of tensors shaped [..., E_global, ...] in global env order (None on ranks other
+    than `dst` when gathering to one rank).  One collective per tensor, no per-step traffic.
+    """
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return tuple(tensors)
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    out = []
+    for t in tensors:
+        t = t.contiguous()
+        if equal_shards:
+            if dst is None:
+                # concatenated-along-dim-0 output form (accepted by both NCCL and gloo)
+                buf = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+                dist.all_gather_into_tensor(buf, t, group=group)
+                parts = list(buf.view((world,) + tuple(t.shape)).unbind(0))
+            else:
+                parts = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+                dist.gather(t, parts, dst=dst, group=group)
+        else:  # ragged shards: exchange sizes, pad to the largest shard, gather, trim
+            n = torch.tensor([t.shape[env_dim]], dtype=torch.int64, device=t.device)
+            sizes = torch.empty(world, dtype=torch.int64, device=t.device)
+            dist.all_gather_into_tensor(sizes, n, group=group)
+            sizes = [int(v) for v in sizes.tolist()]
+            shp = list(t.shape)
+            shp[env_dim] = max(sizes)
+            padded = torch.zeros(shp, dtype=t.dtype, device=t.device)
+            padded.narrow(env_dim, 0, t.shape[env_dim]).copy_(t)
+            buf = torch.empty((world * shp[0],) + tuple(shp[1:]), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(buf, padded, group=group)
+            parts = [c.narrow(env_dim, 0, sz) for c, sz in zip(buf.view([world] + shp).unbind(0), sizes)]
+        out.append(torch.cat(parts, dim=env_dim) if parts is not None else None)
+    return tuple(out)
