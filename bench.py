@@ -178,10 +178,10 @@ def main():
            torch.empty((T, E), dtype=torch.uint8, device=dev),
            torch.empty((T, E, 2), dtype=torch.int32, device=dev))
     if world > 1:
-        g_rew = torch.empty((world,) + tuple(out[1].shape), device=dev)
-        g_done = torch.empty((world,) + tuple(out[2].shape), dtype=torch.uint8, device=dev)
-        g_info = torch.empty((world,) + tuple(out[3].shape), dtype=torch.int32, device=dev)
-        g_obs = torch.empty((world,) + tuple(out[0].shape), device=dev) if a.gather_obs else None
+        def gbuf(x):   # all_gather_into_tensor output: ranks concatenated along dim 0
+            return torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)
+        g_rew, g_done, g_info = gbuf(out[1]), gbuf(out[2]), gbuf(out[3])
+        g_obs = gbuf(out[0]) if a.gather_obs else None
 
     def one_step(i):
         eng.rollout(actions[i % n_act], auto_reset=True, out=out)
