@@ -121,14 +121,15 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
     real* rew_t = p.rew + (size_t)e * p.Nr + lane;
     size_t te = (size_t)e;
     int pass = (p.mode == 1) ? 1 : 0;
-    V2 act_next;
-    act_next.x = 0; act_next.y = 0;
-    if (p.mode == 0 && lane < p.Nr) act_next = reinterpret_cast<const V2*>(p.actions)[(size_t)e * p.Nr + lane];
+    const V2* act_t = reinterpret_cast<const V2*>(p.actions) + (size_t)e * p.Nr + lane;
 
     for (int t = 0; t < p.T; ++t) {
-      V2 act = act_next;
-      if (p.mode == 0 && t + 1 < p.T && lane < p.Nr)
-        act_next = reinterpret_cast<const V2*>(p.actions)[((size_t)(t + 1) * p.E + e) * p.Nr + lane];
+      V2 act;
+      act.x = 0; act.y = 0;
+      if (p.mode == 0 && lane < p.Nr) {
+        act = *act_t;
+        if (t + 1 < p.T) prefetch_l1(act_t + (size_t)p.E * p.Nr);   // next step's action -> L1
+      }
       bool need_reset;
       do {
         if (pass) {
@@ -380,6 +381,7 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
         pass = need_reset ? 1 : 0;
       } while (need_reset);
       obs_t += step_stride;
+      act_t += (size_t)p.E * p.Nr;
       rew_t += (size_t)p.E * p.Nr;
       te += (size_t)p.E;
     }

@@ -94,9 +94,13 @@ __global__ void __launch_bounds__(128, 7) pe_kernel(const __grid_constant__ PEPa
   const int R = RC > 0 ? RC : p.R, RR = R * R, xs = p.xs, ys = p.ys, ncell = xs * ys;
   const int Np = p.Np, Ne = p.Ne, Nag = Np + Ne;
 
-  // per-warp shared memory: cell words, then the stale window counts
-  uint32_t* cellw = smem_u32 + (size_t)wib * (p.smem_per_warp / 4);
-  uint16_t* stale = reinterpret_cast<uint16_t*>(cellw + p.cells_pad);
+  // shared memory: block-wide count->value table, then per warp: cell words, stale window counts
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<float*>(smem_u32)[i] = p.lut[i];
+  __syncthreads();   // the only block barrier: once, before the persistent loop
+  const uint32_t lut_a = smem_addr(smem_u32);
+  const uint32_t cell_a = lut_a + 1024u + (uint32_t)wib * (uint32_t)p.smem_per_warp;
+  const uint32_t stale_a = cell_a + 4u * (uint32_t)p.cells_pad;
+  const float my_idv = (lane < p.Np) ? p.idv[lane] : 0.0f;   // lane i keeps float32(i / Np)
 
   // per-lane window cell offsets
   int wdx[CPL], wdy[CPL];
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(128, 7) pe_kernel(const __grid_constant__ PEPa
     int map_id = p.map_id[e], ts = p.path_len[e];
     uint64_t ctr = p.ctr[e];
     const uint8_t* map = p.maps + (size_t)map_id * ncell;
-    for (int i = lane; i < Np * RR; i += 32) stale[i] = p.stale[(size_t)e * Np * RR + i];
+    for (int i = lane; i < Np * RR; i += 32) sts_u16(stale_a + 2u * i, p.stale[(size_t)e * Np * RR + i]);
     bool rebuild = true;   // cell words must be (re)built from map + positions
 
     float* obs_t = p.obs + (size_t)e * Np * p.D;
@@ -137,12 +141,12 @@ __global__ void __launch_bounds__(128, 7) pe_kernel(const __grid_constant__ PEPa
     const int32_t* act_t = p.actions + (size_t)e * Np + lane;
     size_t te = (size_t)e;
     int pass = (p.mode == 1) ? 1 : 0;   // pass 1 = reset(): draws + obs only
-    int act_next = 4;
-    if (p.mode == 0 && lane < Np) act_next = *act_t;
-
     for (int t = 0; t < p.T; ++t) {
-      int act = act_next;
-      if (p.mode == 0 && t + 1 < p.T && lane < Np) act_next = act_t[(size_t)p.E * Np];
+      int act = 4;
+      if (p.mode == 0 && lane < Np) {
+        act = *act_t;
+        if (t + 1 < p.T) prefetch_l1(act_t + (size_t)p.E * Np);   // next step's action -> L1
+      }
       bool need_reset;
       do {
         int removed = 0;
@@ -183,12 +187,12 @@ __global__ void __launch_bounds__(128, 7) pe_kernel(const __grid_constant__ PEPa
         }
         if (rebuild) {   // cell words from scratch: building flag + occupancy counts
           __syncwarp();
-          for (int i = lane; i < ncell; i += 32) cellw[i] = map[i] ? 1u : 0u;
+          for (int i = lane; i < ncell; i += 32) sts_u32(cell_a + 4u * i, map[i] ? 1u : 0u);
           __syncwarp();
-          if (lane < Np) atomicAdd(&cellw[px * ys + py], 1u << 8);
+          if (lane < Np) reds_add_u32(cell_a + 4u * (px * ys + py), 1u << 8);
 #pragma unroll
           for (int c = 0; c < EPL; ++c)
-            if ((live[c] >> lane) & 1u) atomicAdd(&cellw[ex[c] * ys + ey[c]], 1u << 16);
+            if ((live[c] >> lane) & 1u) reds_add_u32(cell_a + 4u * (ex[c] * ys + ey[c]), 1u << 16);
           __syncwarp();
           rebuild = false;
         }
@@ -197,19 +201,22 @@ __global__ void __launch_bounds__(128, 7) pe_kernel(const __grid_constant__ PEPa
           if (lane < Np) {
             const int xm = max(px - 1, 0), xp = min(px + 1, xs - 1);
             const int ym = max(py - 1, 0), yp = min(py + 1, ys - 1);
-            rcount = (int)((cellw[xm * ys + py] >> 16) & 0xff) + (int)((cellw[xp * ys + py] >> 16) & 0xff) +
-                     (int)((cellw[px * ys + yp] >> 16) & 0xff) + (int)((cellw[px * ys + ym] >> 16) & 0xff);
+            rcount = (int)((lds_u32(cell_a + 4u * (xm * ys + py)) >> 16) & 0xff) +
+                     (int)((lds_u32(cell_a + 4u * (xp * ys + py)) >> 16) & 0xff) +
+                     (int)((lds_u32(cell_a + 4u * (px * ys + yp)) >> 16) & 0xff) +
+                     (int)((lds_u32(cell_a + 4u * (px * ys + ym)) >> 16) & 0xff);
           }
           __syncwarp();
           // ---- move pursuers: pe:227-235, da:69-97 ---------------------------------------------
           if (lane < Np) {
             const int a = act;
             const int dx = (a == 0) ? -1 : (a == 1 ? 1 : 0), dy = (a == 2) ? 1 : (a == 3 ? -1 : 0);
-            const int nx = px + dx, ny = py + dy, cur = px * ys + py;
+            const int nx = px + dx, ny = py + dy;
+            const uint32_t cur = cell_a + 4u * (px * ys + py), nxt = cell_a + 4u * (nx * ys + ny);
             if ((unsigned)a < 4u && (unsigned)nx < (unsigned)xs && (unsigned)ny < (unsigned)ys &&
-                (cellw[cur] & 0xff) == 0u && (cellw[nx * ys + ny] & 0xff) == 0u) {
-              atomicSub(&cellw[cur], 1u << 8);
-              atomicAdd(&cellw[nx * ys + ny], 1u << 8);
+                (lds_u32(cur) & 0xff) == 0u && (lds_u32(nxt) & 0xff) == 0u) {
+              reds_add_u32(cur, 0u - (1u << 8));
+              reds_add_u32(nxt, 1u << 8);
               px = nx; py = ny;
             }
           }
@@ -222,11 +229,12 @@ __global__ void __launch_bounds__(128, 7) pe_kernel(const __grid_constant__ PEPa
             if (alive) {
               const int a = u32_to_range(stream_word(p.seed, env_id, 0u, ctr + (uint64_t)rank), 0, 5);
               const int dx = (a == 0) ? -1 : (a == 1 ? 1 : 0), dy = (a == 2) ? 1 : (a == 3 ? -1 : 0);
-              const int nx = ex[c] + dx, ny = ey[c] + dy, cur = ex[c] * ys + ey[c];
+              const int nx = ex[c] + dx, ny = ey[c] + dy;
+              const uint32_t cur = cell_a + 4u * (ex[c] * ys + ey[c]), nxt = cell_a + 4u * (nx * ys + ny);
               if (a < 4 && (unsigned)nx < (unsigned)xs && (unsigned)ny < (unsigned)ys &&
-                  (cellw[cur] & 0xff) == 0u && (cellw[nx * ys + ny] & 0xff) == 0u) {
-                atomicSub(&cellw[cur], 1u << 16);
-                atomicAdd(&cellw[nx * ys + ny], 1u << 16);
+                  (lds_u32(cur) & 0xff) == 0u && (lds_u32(nxt) & 0xff) == 0u) {
+                reds_add_u32(cur, 0u - (1u << 16));
+                reds_add_u32(nxt, 1u << 16);
                 ex[c] = nx; ey[c] = ny;
               }
             }
@@ -249,7 +257,7 @@ __global__ void __launch_bounds__(128, 7) pe_kernel(const __grid_constant__ PEPa
                 for (int m = 0; m < 4; ++m) {
                   const int xn = x + (m == 0 ? -1 : (m == 1 ? 1 : 0)), yn = y + (m == 2 ? 1 : (m == 3 ? -1 : 0));
                   if ((unsigned)xn < (unsigned)xs && (unsigned)yn < (unsigned)ys) {
-                    const uint32_t wv = cellw[xn * ys + yn];
+                    const uint32_t wv = lds_u32(cell_a + 4u * (xn * ys + yn));
                     if ((wv >> 8) & 0xff) adj += 1;
                     // pe:536 skips neighbours with xn <= 0 or yn <= 0: row/column 0 never subtracts
                     if (xn > 0 && yn > 0 && (wv & 0xff)) need -= 1;
@@ -257,7 +265,7 @@ __global__ void __launch_bounds__(128, 7) pe_kernel(const __grid_constant__ PEPa
                 }
                 got = (adj == need);
               } else {
-                got = (int)((cellw[x * ys + y] >> 8) & 0xff) >= p.n_catch;            // pe:498
+                got = (int)((lds_u32(cell_a + 4u * (x * ys + y)) >> 8) & 0xff) >= p.n_catch;   // pe:498
               }
             }
             caught[c] = __ballot_sync(FULL_MASK, got);
@@ -275,32 +283,44 @@ __global__ void __launch_bounds__(128, 7) pe_kernel(const __grid_constant__ PEPa
         // ---- collect_obs: pe:418-461 (flatten): channel-major, then x, then y, then id ----------
         {
           float* row = obs_t;
-          uint16_t* st_row = stale;
-          for (int i = 0; i < Np; ++i, row += p.D, st_row += RR) {
+          uint32_t st_row = stale_a;
+          for (int i = 0; i < Np; ++i, row += p.D, st_row += 2u * RR) {
             const int pxi = __shfl_sync(FULL_MASK, px, i), pyi = __shfl_sync(FULL_MASK, py, i);
+            const float idval = __shfl_sync(FULL_MASK, my_idv, i);
+            // explicit software pipeline over the (unrolled) window chunks: all shared loads
+            // first, then the dependent table lookups, then the coalesced stores
+            uint32_t wv[CPL], c12[CPL];
+            bool inb[CPL];
+#pragma unroll
+            for (int it = 0; it < CPL; ++it) {
+              const int w = lane + 32 * it;
+              const int cx = pxi + wdx[it], cy = pyi + wdy[it];
+              // cells beyond 2*off (even obs_range) are never written: treated as out of bounds
+              inb[it] = w < RR && (unsigned)cx < (unsigned)xs && (unsigned)cy < (unsigned)ys &&
+                        wdx[it] <= p.off && wdy[it] <= p.off;
+              wv[it] = inb[it] ? lds_u32(cell_a + 4u * (cx * ys + cy)) : 0u;
+              c12[it] = (w < RR) ? lds_u16(st_row + 2u * w) : 0u;       // stale pursuer | evader << 8
+            }
+            float v1[CPL], v2[CPL];
+#pragma unroll
+            for (int it = 0; it < CPL; ++it) {
+              const int w = lane + 32 * it;
+              if (inb[it]) c12[it] = (wv[it] >> 8) & 0xffffu;
+              if (w < RR) sts_u16(st_row + 2u * w, c12[it]);
+              v1[it] = lds_f32(lut_a + 4u * (c12[it] & 0xffu));         // float32(k) / float32(layer_norm)
+              v2[it] = lds_f32(lut_a + 4u * (c12[it] >> 8));
+            }
 #pragma unroll
             for (int it = 0; it < CPL; ++it) {
               const int w = lane + 32 * it;
               if (w < RR) {
-                const int cx = pxi + wdx[it], cy = pyi + wdy[it];
-                // cells beyond 2*off (even obs_range) are never written: treated as out of bounds
-                const bool inb = (unsigned)cx < (unsigned)xs && (unsigned)cy < (unsigned)ys &&
-                                 wdx[it] <= p.off && wdy[it] <= p.off;
-                uint32_t wv = 0u;
-                if (inb) wv = cellw[cx * ys + cy];
-                const uint32_t sv = st_row[w];
-                const uint32_t c1 = inb ? ((wv >> 8) & 0xff) : (sv & 0xff);
-                const uint32_t c2 = inb ? ((wv >> 16) & 0xff) : (sv >> 8);
-                st_row[w] = (uint16_t)(c1 | (c2 << 8));
-                const float v0 = inb ? ((wv & 0xff) ? p.one_val : 0.0f) : p.wall_val;     // pe:433,438
-                const float v1 = c1 == 0u ? 0.0f : (c1 == 1u ? p.one_val : p.lut[c1]);
-                const float v2 = c2 == 0u ? 0.0f : (c2 == 1u ? p.one_val : p.lut[c2]);
+                const float v0 = inb[it] ? ((wv[it] & 0xff) ? p.one_val : 0.0f) : p.wall_val;   // pe:433,438
                 store_stream(row + w, v0);
-                store_stream(row + RR + w, v1);
-                store_stream(row + 2 * RR + w, v2);
+                store_stream(row + RR + w, v1[it]);
+                store_stream(row + 2 * RR + w, v2[it]);
               }
             }
-            if (lane < n_tail) store_stream(row + 3 * RR, p.idv[i]);                        // pe:444-445
+            if (lane < n_tail) store_stream(row + 3 * RR, idval);                           // pe:444-445
           }
         }
         need_reset = false;
@@ -324,7 +344,7 @@ __global__ void __launch_bounds__(128, 7) pe_kernel(const __grid_constant__ PEPa
           int n_live = 0;
 #pragma unroll
           for (int c = 0; c < EPL; ++c) {
-            if ((caught[c] >> lane) & 1u) atomicSub(&cellw[ex[c] * ys + ey[c]], 1u << 16);
+            if ((caught[c] >> lane) & 1u) reds_add_u32(cell_a + 4u * (ex[c] * ys + ey[c]), 0u - (1u << 16));
             live[c] &= ~caught[c];
             n_live += __popc(live[c]);
           }
@@ -356,7 +376,7 @@ __global__ void __launch_bounds__(128, 7) pe_kernel(const __grid_constant__ PEPa
       const unsigned valid = __ballot_sync(FULL_MASK, j < Ne);
       gone |= (uint64_t)(valid & ~live[c]) << (32 * c);
     }
-    for (int i = lane; i < Np * RR; i += 32) p.stale[(size_t)e * Np * RR + i] = stale[i];
+    for (int i = lane; i < Np * RR; i += 32) p.stale[(size_t)e * Np * RR + i] = (uint16_t)lds_u16(stale_a + 2u * i);
     if (lane == 0) { p.gone[e] = gone; p.map_id[e] = map_id; p.path_len[e] = ts; p.ctr[e] = ctr; }
     __syncwarp();
   }
@@ -493,7 +513,7 @@ extern "C" int madrl_pursuit_set_params(madrl_pursuit* h, double catchr, double 
 template <int EPL, int CPL, int RC>
 static int pe_launch_inst(madrl_pursuit* h, PEParams& p, cudaStream_t stream) {
   const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 4;
-  const size_t smem = (size_t)wpb * p.smem_per_warp;
+  const size_t smem = 1024 + (size_t)wpb * p.smem_per_warp;   // block LUT + per-warp regions
   MADRL_REQUIRE(smem <= 200 * 1024, "map too large for shared memory (%zu B per block)", smem);
   if (smem > 48 * 1024)
     MADRL_CUDA_CHECK(cudaFuncSetAttribute(pe_kernel<EPL, CPL, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -165,14 +165,15 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     real* rew_t = p.rew + (size_t)e * p.Np + lane;
     size_t te = (size_t)e;   // index of (t, e) in the [T][E] done / info tensors
     int pass = (p.mode == 1) ? 1 : 0;  // pass 1 = reset pass: fresh draws, zero action, obs only
-    V2 act_next;
-    act_next.x = 0; act_next.y = 0;
-    if (p.mode == 0 && lane < p.Np) act_next = reinterpret_cast<const V2*>(p.actions)[(size_t)e * p.Np + lane];
+    const V2* act_t = reinterpret_cast<const V2*>(p.actions) + (size_t)e * p.Np + lane;
 
     for (int t = 0; t < p.T; ++t) {
-      V2 act = act_next;
-      if (p.mode == 0 && t + 1 < p.T && lane < p.Np)  // prefetch the next step's action
-        act_next = reinterpret_cast<const V2*>(p.actions)[((size_t)(t + 1) * p.E + e) * p.Np + lane];
+      V2 act;
+      act.x = 0; act.y = 0;
+      if (p.mode == 0 && lane < p.Np) {
+        act = *act_t;
+        if (t + 1 < p.T) prefetch_l1(act_t + (size_t)p.E * p.Np);   // next step's action -> L1
+      }
       bool need_reset;
       do {
         if (pass) {
@@ -383,6 +384,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
         pass = need_reset ? 1 : 0;
       } while (need_reset);
       obs_t += step_stride;
+      act_t += (size_t)p.E * p.Np;
       rew_t += (size_t)p.E * p.Np;
       te += (size_t)p.E;
     }
