@@ -133,7 +133,7 @@ def lib():
     """Load (building if needed) the CUDA library.  Raises EngineError on failure."""
     global _lib
     if _lib is None:
-        path = _build.LIB
+        path = os.environ.get("MADRL_B200_LIB", _build.LIB)   # override: kernel-variant experiments
         if not os.path.exists(path) or os.environ.get("MADRL_B200_REBUILD"):
             try:
                 path = _build.build()

@@ -218,92 +218,94 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
         for (int pi = 0; pi < p.Nr; ++pi, obs_row += p.D) {
           const real mx = __shfl_sync(FULL_MASK, x[0], pi), my = __shfl_sync(FULL_MASK, y[0], pi);
           const real mvx = __shfl_sync(FULL_MASK, vx[0], pi), mvy = __shfl_sync(FULL_MASK, vy[0], pi);
-          real rx[OPL], ry[OPL], d2[OPL];
-          unsigned cm[OPL];
-          unsigned hitC = 0u, hitH = 0u;
-#pragma unroll
-          for (int c = 0; c < OPL; ++c) {
-            rx[c] = x[c] - mx; ry[c] = y[c] - my;
-            d2[c] = rx[c] * rx[c] + ry[c] * ry[c];
-            // saved hostages are invisible (pre-step mask, hw:301) but still collide (hw:269-275)
-            cm[c] = __ballot_sync(FULL_MASK, d2[c] <= cull2_l[c] && !sav[c]);
-            const bool hit = d2[c] <= coll2_l[c];
-            const unsigned hb = __ballot_sync(FULL_MASK, hit);
-            if (hit) col[c] |= 1u << pi;
-            hitC |= hb & mC[c];
-            hitH |= hb & mH[c];
-          }
           const real krx = kx - mx, kry = ky - my, kd2 = krx * krx + kry * kry;
           const real brx = bx - mx, bry = by - my, bd2 = brx * brx + bry * bry;
+          real bK[KCH], bB[KCH], bC[KCH], bH[KCH];
+          int iC[KCH];
 #pragma unroll
           for (int kc = 0; kc < KCH; ++kc) {
+            bK[kc] = bB[kc] = bC[kc] = bH[kc] = INF;
+            iC[kc] = 0;
             const real sx = sx_l[kc], sy = sy_l[kc];
-            real bK = INF, bB = INF, bC = INF, bH = INF;
-            int iC = 0;
             if (!gate_pre && kd2 <= p.cull2) {                                    // hw:343-345
               const real sv = sx * krx + sy * kry;
               const bool ok = !((sv < (real)0) | (sv > p.range) | (kd2 - sv * sv > p.r_r2));
-              bK = ok ? sv : INF;
+              bK[kc] = ok ? sv : INF;
             }
             if (bd2 <= p.cull2) {
               const real sv = sx * brx + sy * bry;
               const bool ok = !((sv < (real)0) | (sv > p.range) | (bd2 - sv * sv > p.r_r2));
-              bB = ok ? sv : INF;
+              bB[kc] = ok ? sv : INF;
             }
+          }
+          unsigned hitC = 0u, hitH = 0u;
 #pragma unroll
-            for (int c = 0; c < OPL; ++c) {
-              for (unsigned m = cm[c] & mC[c]; m != 0u; m &= m - 1u) {
+          for (int c = 0; c < OPL; ++c) {
+            const real rx = x[c] - mx, ry = y[c] - my;
+            const real d2 = rx * rx + ry * ry;
+            // saved hostages are invisible (pre-step mask, hw:301) but still collide (hw:269-275)
+            const unsigned cm = __ballot_sync(FULL_MASK, d2 <= cull2_l[c] && !sav[c]);
+            const bool hit = d2 <= coll2_l[c];
+            const unsigned hb = __ballot_sync(FULL_MASK, hit);
+            if (hit) col[c] |= 1u << pi;
+            hitC |= hb & mC[c];
+            hitH |= hb & mH[c];
+#pragma unroll
+            for (int kc = 0; kc < KCH; ++kc) {
+              const real sx = sx_l[kc], sy = sy_l[kc];
+              for (unsigned m = cm & mC[c]; m != 0u; m &= m - 1u) {
                 const int j = __ffs(m) - 1;
-                const real jx = __shfl_sync(FULL_MASK, rx[c], j), jy = __shfl_sync(FULL_MASK, ry[c], j);
-                const real jd = __shfl_sync(FULL_MASK, d2[c], j);
+                const real jx = __shfl_sync(FULL_MASK, rx, j), jy = __shfl_sync(FULL_MASK, ry, j);
+                const real jd = __shfl_sync(FULL_MASK, d2, j);
                 const real sv = sx * jx + sy * jy;
                 const bool ok = !((sv < (real)0) | (sv > p.range) | (jd - sv * sv > p.r_r2));
-                if (ok && sv < bC) { bC = sv; iC = j + 32 * c; }
+                if (ok && sv < bC[kc]) { bC[kc] = sv; iC[kc] = j + 32 * c; }
               }
               if (gate_pre) {                                                      // hw:323-325
-                for (unsigned m = cm[c] & mH[c]; m != 0u; m &= m - 1u) {
+                for (unsigned m = cm & mH[c]; m != 0u; m &= m - 1u) {
                   const int j = __ffs(m) - 1;
-                  const real jx = __shfl_sync(FULL_MASK, rx[c], j), jy = __shfl_sync(FULL_MASK, ry[c], j);
-                  const real jd = __shfl_sync(FULL_MASK, d2[c], j);
+                  const real jx = __shfl_sync(FULL_MASK, rx, j), jy = __shfl_sync(FULL_MASK, ry, j);
+                  const real jd = __shfl_sync(FULL_MASK, d2, j);
                   const real sv = sx * jx + sy * jy;
                   const bool ok = !((sv < (real)0) | (sv > p.range) | (jd - sv * sv > p.r_r2));
-                  if (ok && sv < bH) bH = sv;
+                  if (ok && sv < bH[kc]) bH[kc] = sv;
                 }
               }
             }
+          }
+#pragma unroll
+          for (int kc = 0; kc < KCH; ++kc) {
+            const real sx = sx_l[kc], sy = sy_l[kc];
             // features hw:395-397: [criminal dist, criminal speed, hostage dist, key dist, bomb dist]
             const int k = lane + 32 * kc;
             const real z = (real)0;
             real oCx, oCy;
             if (OPL == 1) {
-              oCx = __shfl_sync(FULL_MASK, vx[0], iC); oCy = __shfl_sync(FULL_MASK, vy[0], iC);
+              oCx = __shfl_sync(FULL_MASK, vx[0], iC[kc]); oCy = __shfl_sync(FULL_MASK, vy[0], iC[kc]);
             } else {
               oCx = oCy = z;
 #pragma unroll
               for (int c = 0; c < OPL; ++c) {
-                const real cx_ = __shfl_sync(FULL_MASK, vx[c], iC & 31), cy_ = __shfl_sync(FULL_MASK, vy[c], iC & 31);
-                if ((iC >> 5) == c) { oCx = cx_; oCy = cy_; }
+                const real cx_ = __shfl_sync(FULL_MASK, vx[c], iC[kc] & 31), cy_ = __shfl_sync(FULL_MASK, vy[c], iC[kc] & 31);
+                if ((iC[kc] >> 5) == c) { oCx = cx_; oCy = cy_; }
               }
             }
             if (k < K) {
               real* o = obs_row + 32 * kc;
-              const bool hC = bC < INF;
-              store_stream(o + 0 * K, hC ? bC : z);
+              const bool hC = bC[kc] < INF;
+              store_stream(o + 0 * K, hC ? bC[kc] : z);
               store_stream(o + 1 * K, hC ? sx * (oCx - mvx) + sy * (oCy - mvy) : z);
-              store_stream(o + 2 * K, bH < INF ? bH : z);
-              store_stream(o + 3 * K, bK < INF ? bK : z);
-              store_stream(o + 4 * K, bB < INF ? bB : z);
+              store_stream(o + 2 * K, bH[kc] < INF ? bH[kc] : z);
+              store_stream(o + 3 * K, bK[kc] < INF ? bK[kc] : z);
+              store_stream(o + 4 * K, bB[kc] < INF ? bB[kc] : z);
             }
           }
-          // tail hw:406-421: coll_ho, coll_cr, coll_key, coll_bomb, gate_open (post), id
+          // tail hw:406-421: coll_ho, coll_cr, coll_key, coll_bomb, gate_open (post), id -- one
+          // branch-free store
           if (lane < n_tail) {
-            real tv;
-            if (lane == 0) tv = hitH ? (real)1 : (real)0;
-            else if (lane == 1) tv = hitC ? (real)1 : (real)0;
-            else if (lane == 2) tv = ((coll_ke >> pi) & 1u) ? (real)1 : (real)0;
-            else if (lane == 3) tv = ((coll_bo >> pi) & 1u) ? (real)1 : (real)0;
-            else if (lane == 4) tv = gate_post ? (real)1 : (real)0;
-            else tv = (real)(pi + 1);
+            const unsigned bits = (hitH ? 1u : 0u) | (hitC ? 2u : 0u) | (((coll_ke >> pi) & 1u) << 2) |
+                                  (((coll_bo >> pi) & 1u) << 3) | (gate_post ? 16u : 0u);
+            const real tv = lane < 5 ? (real)((bits >> lane) & 1u) : (real)(pi + 1);
             store_stream(obs_row + 5 * K, tv);
           }
         }

@@ -99,8 +99,11 @@ __device__ __noinline__ Spawn<real> spawn_object(uint64_t seed, uint32_t env_id,
 // OPL = objects per lane (ceil(n_obj / 32)); KCH = sensors per lane (ceil(K / 32));
 // KC = compile-time sensor count (0 = runtime p.K): with KC known the 7 feature-row stores of a
 // pursuer use immediate offsets from one running pointer instead of 64-bit address arithmetic.
+#ifndef MADRL_WW_MINBLOCKS_OPL4
+#define MADRL_WW_MINBLOCKS_OPL4 7   // resident 128-thread blocks per SM requested for 65..128 objects
+#endif
 template <typename real, int OPL, int KCH, int KC>
-__global__ void __launch_bounds__(128, (OPL <= 2 ? 7 : 4))
+__global__ void __launch_bounds__(128, (OPL <= 2 ? 7 : (OPL <= 4 ? MADRL_WW_MINBLOCKS_OPL4 : 4)))
 ww_kernel(const __grid_constant__ WWParams<real> p) {
   const real INF = real_inf<real>();
   const int K = KC > 0 ? KC : p.K;
@@ -111,8 +114,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
   const int eLo = p.Np, eHi = p.Np + p.Ne, Nall = p.Nall;
 
   // ---- per-lane constants: this lane as OBJECT (classes, thresholds) and as SENSOR -----------
-  real cull2_l[OPL], coll2_l[OPL], obst2_l[OPL], kf_l[OPL];
-  int need_l[OPL];               // collisions needed to be caught (ww:285: n_coop, ww:293: 1)
+  real cull2_l[OPL], coll2_l[OPL];
   unsigned mE[OPL], mP[OPL], mU[OPL];  // warp-uniform class masks of each object chunk
 #pragma unroll
   for (int c = 0; c < OPL; ++c) {
@@ -120,9 +122,6 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     const bool isU = o < eLo, isE = o >= eLo && o < eHi, isP = o >= eHi && o < Nall;
     cull2_l[c] = (o < Nall) ? p.cull2 : (real)-1;
     coll2_l[c] = isE ? p.coll2_e : (isP ? p.coll2_po : (real)-1);
-    obst2_l[c] = isU ? p.obst2_p : (isE ? p.obst2_e : (isP ? p.obst2_po : (real)-1));
-    kf_l[c] = isP ? (real)-1 : (real)-0.5;                      // ww:254,262,270
-    need_l[c] = isE ? p.n_coop : (isP ? 1 : 0x7fffffff);
     mU[c] = __ballot_sync(FULL_MASK, isU);
     mE[c] = __ballot_sync(FULL_MASK, isE);
     mP[c] = __ballot_sync(FULL_MASK, isP);
@@ -220,102 +219,110 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
         // ---- obstacle rebound (velocity only): ww:247-270 ----------------------------------------
 #pragma unroll
         for (int c = 0; c < OPL; ++c) {
+          const bool oE = (mE[c] >> lane) & 1u, oP = (mP[c] >> lane) & 1u, oU = (mU[c] >> lane) & 1u;
+          const real thr = oU ? p.obst2_p : (oE ? p.obst2_e : (oP ? p.obst2_po : (real)-1));
+          const real kf = oP ? (real)-1 : (real)-0.5;                  // ww:254,262,270
           const real dx = x[c] - obx, dy = y[c] - oby;
-          if (dx * dx + dy * dy <= obst2_l[c]) { vx[c] = kf_l[c] * vx[c]; vy[c] = kf_l[c] * vy[c]; }
+          if (dx * dx + dy * dy <= thr) { vx[c] = kf * vx[c]; vy[c] = kf * vy[c]; }
         }
         // ---- sense: one pursuer at a time -----------------------------------------------------
         real* obs_row = obs_t;
         for (int pi = 0; pi < p.Np; ++pi, obs_row += p.D) {
           const real mx = __shfl_sync(FULL_MASK, x[0], pi), my = __shfl_sync(FULL_MASK, y[0], pi);
           const real mvx = __shfl_sync(FULL_MASK, vx[0], pi), mvy = __shfl_sync(FULL_MASK, vy[0], pi);
-          // lanes as objects: geometry, collisions (ww:278-293), conservative range cull
-          real rx[OPL], ry[OPL], d2[OPL];
-          unsigned cm[OPL];
-          unsigned hitE = 0u, hitP = 0u;
-#pragma unroll
-          for (int c = 0; c < OPL; ++c) {
-            rx[c] = x[c] - mx; ry[c] = y[c] - my;
-            d2[c] = rx[c] * rx[c] + ry[c] * ry[c];
-            cm[c] = __ballot_sync(FULL_MASK, d2[c] <= cull2_l[c]);
-            const bool hit = d2[c] <= coll2_l[c];
-            const unsigned hb = __ballot_sync(FULL_MASK, hit);
-            if (hit) col[c] |= 1u << pi;
-            hitE |= hb & mE[c];
-            hitP |= hb & mP[c];
-          }
-          cm[0] &= ~(1u << pi);  // ww:70-71 `same`
+          // nearest sensed object per class and sensor chunk (ww:64-72, 312-334)
+          real bO[KCH], bE[KCH], bP[KCH], bU[KCH];
+          int iE[KCH], iP[KCH], iU[KCH];
           const real orx = obx - mx, ory = oby - my;
           const real od2 = orx * orx + ory * ory;
 #pragma unroll
           for (int kc = 0; kc < KCH; ++kc) {
-            const real sx = sx_l[kc], sy = sy_l[kc];
-            // lanes as sensors: nearest sensed object per class (ww:64-72, 312-334)
-            real bO = INF, bE = INF, bP = INF, bU = INF;
-            int iE = 0, iP = 0, iU = 0;
-            if (od2 <= p.cull2) {
-              const real sv = sx * orx + sy * ory;
+            bO[kc] = bE[kc] = bP[kc] = bU[kc] = INF;
+            iE[kc] = iP[kc] = iU[kc] = 0;
+            if (od2 <= p.cull2) {   // the obstacle is sensed like a point object (pursuer radius only)
+              const real sv = sx_l[kc] * orx + sy_l[kc] * ory;
               const bool ok = !((sv < (real)0) | (sv > p.range) | (od2 - sv * sv > p.r_p2));
-              bO = ok ? sv : INF;
+              bO[kc] = ok ? sv : INF;
             }
+          }
+          unsigned hitE = 0u, hitP = 0u;
 #pragma unroll
-            for (int c = 0; c < OPL; ++c) {
-#define MADRL_WW_SCAN(MASK, BEST, IDX)                                                      \
-  for (unsigned m = cm[c] & (MASK); m != 0u; m &= m - 1u) {                                  \
-    const int j = __ffs(m) - 1;                                                              \
-    const real jx = __shfl_sync(FULL_MASK, rx[c], j), jy = __shfl_sync(FULL_MASK, ry[c], j); \
-    const real jd = __shfl_sync(FULL_MASK, d2[c], j);                                        \
-    const real sv = sx * jx + sy * jy;                                                       \
-    const bool ok = !((sv < (real)0) | (sv > p.range) | (jd - sv * sv > p.r_p2));            \
-    if (ok && sv < BEST) { BEST = sv; IDX = j + 32 * c; }                                    \
+          for (int c = 0; c < OPL; ++c) {
+            // lanes as OBJECTS: geometry, collisions (ww:278-293), conservative range cull
+            const real rx = x[c] - mx, ry = y[c] - my;
+            const real d2 = rx * rx + ry * ry;
+            unsigned cm = __ballot_sync(FULL_MASK, d2 <= cull2_l[c]);
+            if (c == 0) cm &= ~(1u << pi);  // ww:70-71 `same`
+            const bool hit = d2 <= coll2_l[c];
+            const unsigned hb = __ballot_sync(FULL_MASK, hit);
+            if (hit) col[c] |= 1u << pi;
+            hitE |= hb & mE[c];
+            hitP |= hb & mP[c];
+            // lanes as SENSORS: scan the surviving candidates of this chunk, ascending index
+#pragma unroll
+            for (int kc = 0; kc < KCH; ++kc) {
+              const real sx = sx_l[kc], sy = sy_l[kc];
+#define MADRL_WW_SCAN(MASK, BEST, IDX)                                                  \
+  for (unsigned m = cm & (MASK); m != 0u; m &= m - 1u) {                                 \
+    const int j = __ffs(m) - 1;                                                          \
+    const real jx = __shfl_sync(FULL_MASK, rx, j), jy = __shfl_sync(FULL_MASK, ry, j);   \
+    const real jd = __shfl_sync(FULL_MASK, d2, j);                                       \
+    const real sv = sx * jx + sy * jy;                                                   \
+    const bool ok = !((sv < (real)0) | (sv > p.range) | (jd - sv * sv > p.r_p2));        \
+    if (ok && sv < BEST) { BEST = sv; IDX = j + 32 * c; }                                \
   }
-              MADRL_WW_SCAN(mU[c], bU, iU)
-              MADRL_WW_SCAN(mE[c], bE, iE)
-              MADRL_WW_SCAN(mP[c], bP, iP)
+              MADRL_WW_SCAN(mU[c], bU[kc], iU[kc])
+              MADRL_WW_SCAN(mE[c], bE[kc], iE[kc])
+              MADRL_WW_SCAN(mP[c], bP[kc], iP[kc])
 #undef MADRL_WW_SCAN
             }
+          }
+#pragma unroll
+          for (int kc = 0; kc < KCH; ++kc) {
+            const real sx = sx_l[kc], sy = sy_l[kc];
             // features ww:312-353, 388-395: feature-major, sensor-minor
             const int k = lane + 32 * kc;
-            const bool hO = bO < INF, hE = bE < INF, hP = bP < INF, hU = bU < INF;
+            const bool hO = bO[kc] < INF, hE = bE[kc] < INF, hP = bP[kc] < INF, hU = bU[kc] < INF;
             const real z = (real)0;
             real* o = obs_row + 32 * kc;   // this lane's column
             if (p.speed_features) {
               real oEx, oEy, oPx, oPy, oUx, oUy;
               if (OPL == 1) {
-                oEx = __shfl_sync(FULL_MASK, vx[0], iE); oEy = __shfl_sync(FULL_MASK, vy[0], iE);
-                oPx = __shfl_sync(FULL_MASK, vx[0], iP); oPy = __shfl_sync(FULL_MASK, vy[0], iP);
-                oUx = __shfl_sync(FULL_MASK, vx[0], iU); oUy = __shfl_sync(FULL_MASK, vy[0], iU);
+                oEx = __shfl_sync(FULL_MASK, vx[0], iE[kc]); oEy = __shfl_sync(FULL_MASK, vy[0], iE[kc]);
+                oPx = __shfl_sync(FULL_MASK, vx[0], iP[kc]); oPy = __shfl_sync(FULL_MASK, vy[0], iP[kc]);
+                oUx = __shfl_sync(FULL_MASK, vx[0], iU[kc]); oUy = __shfl_sync(FULL_MASK, vy[0], iU[kc]);
               } else {
                 oEx = oEy = oPx = oPy = oUx = oUy = z;
 #pragma unroll
                 for (int c = 0; c < OPL; ++c) {
-                  const real ex_ = __shfl_sync(FULL_MASK, vx[c], iE & 31), ey_ = __shfl_sync(FULL_MASK, vy[c], iE & 31);
-                  const real px_ = __shfl_sync(FULL_MASK, vx[c], iP & 31), py_ = __shfl_sync(FULL_MASK, vy[c], iP & 31);
-                  const real ux_ = __shfl_sync(FULL_MASK, vx[c], iU & 31), uy_ = __shfl_sync(FULL_MASK, vy[c], iU & 31);
-                  if ((iE >> 5) == c) { oEx = ex_; oEy = ey_; }
-                  if ((iP >> 5) == c) { oPx = px_; oPy = py_; }
-                  if ((iU >> 5) == c) { oUx = ux_; oUy = uy_; }
+                  const real ex_ = __shfl_sync(FULL_MASK, vx[c], iE[kc] & 31), ey_ = __shfl_sync(FULL_MASK, vy[c], iE[kc] & 31);
+                  const real px_ = __shfl_sync(FULL_MASK, vx[c], iP[kc] & 31), py_ = __shfl_sync(FULL_MASK, vy[c], iP[kc] & 31);
+                  const real ux_ = __shfl_sync(FULL_MASK, vx[c], iU[kc] & 31), uy_ = __shfl_sync(FULL_MASK, vy[c], iU[kc] & 31);
+                  if ((iE[kc] >> 5) == c) { oEx = ex_; oEy = ey_; }
+                  if ((iP[kc] >> 5) == c) { oPx = px_; oPy = py_; }
+                  if ((iU[kc] >> 5) == c) { oUx = ux_; oUy = uy_; }
                 }
               }
               if (k < K) {
-                store_stream(o + 0 * K, hO ? bO : z);
-                store_stream(o + 1 * K, hE ? bE : z);
+                store_stream(o + 0 * K, hO ? bO[kc] : z);
+                store_stream(o + 1 * K, hE ? bE[kc] : z);
                 store_stream(o + 2 * K, hE ? sx * (oEx - mvx) + sy * (oEy - mvy) : z);
-                store_stream(o + 3 * K, hP ? bP : z);
+                store_stream(o + 3 * K, hP ? bP[kc] : z);
                 store_stream(o + 4 * K, hP ? sx * (oPx - mvx) + sy * (oPy - mvy) : z);
-                store_stream(o + 5 * K, hU ? bU : z);
+                store_stream(o + 5 * K, hU ? bU[kc] : z);
                 store_stream(o + 6 * K, hU ? sx * (oUx - mvx) + sy * (oUy - mvy) : z);
               }
             } else if (k < K) {
-              store_stream(o + 0 * K, hO ? bO : z);
-              store_stream(o + 1 * K, hE ? bE : z);
-              store_stream(o + 2 * K, hP ? bP : z);
-              store_stream(o + 3 * K, hU ? bU : z);
+              store_stream(o + 0 * K, hO ? bO[kc] : z);
+              store_stream(o + 1 * K, hE ? bE[kc] : z);
+              store_stream(o + 2 * K, hP ? bP[kc] : z);
+              store_stream(o + 3 * K, hU ? bU[kc] : z);
             }
           }
-          // ww:411-428 tail: collided-with-evader, collided-with-poison, id -- one store
+          // ww:411-428 tail: collided-with-evader, collided-with-poison, id -- one branch-free store
           if (lane < n_tail) {
-            const real tv = lane == 0 ? (hitE ? (real)1 : (real)0)
-                          : (lane == 1 ? (hitP ? (real)1 : (real)0) : (real)(pi + 1));
+            const unsigned bits = (hitE ? 1u : 0u) | (hitP ? 2u : 0u);
+            const real tv = lane < 2 ? (real)((bits >> lane) & 1u) : (real)(pi + 1);
             store_stream(obs_row + n_feat * K, tv);
           }
         }
@@ -325,7 +332,8 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
 #pragma unroll
         for (int c = 0; c < OPL; ++c) {
           const int cnt = __popc(col[c]);
-          const bool caught = cnt >= need_l[c];
+          // collisions needed to be caught: evaders n_coop (ww:285), poisons 1 (ww:293)
+          const bool caught = ((mE[c] >> lane) & 1u) ? cnt >= p.n_coop : (((mP[c] >> lane) & 1u) && cnt >= 1);
           const unsigned cmk = __ballot_sync(FULL_MASK, caught);
           const unsigned enc = __ballot_sync(FULL_MASK, cnt >= 1) & mE[c];   // ww:376
           nE += __popc(cmk & mE[c]);

@@ -33,11 +33,14 @@ def run(E, T, wpb, bps, cfg, reps=5):
 if __name__ == "__main__":
     c2 = dict(n_pursuers=5, n_evaders=5)
     c4 = dict(n_pursuers=20, n_evaders=50, n_poison=50)
-    for wpb, bps in [(4, 0), (2, 0), (1, 0), (4, 4), (4, 2)]:
-        run(4096, 64, wpb, bps, c2)
-    for T in (1, 8, 256):
-        run(4096, T, 4, 0, c2, reps=20 if T == 1 else 5)
-    for E in (2048, 8192, 16384, 65536):
-        run(E, 16, 4, 0, c2)
-    for wpb in (4, 2):
-        run(4096, 16, wpb, 0, c4)
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "c2"):
+        for wpb, bps in [(4, 0), (2, 0)]:
+            run(4096, 64, wpb, bps, c2)
+        for T in (1, 8, 256):
+            run(4096, T, 4, 0, c2, reps=20 if T == 1 else 5)
+        for E in (2048, 8192, 16384, 65536):
+            run(E, 16, 4, 0, c2)
+    if which in ("all", "c4"):
+        run(4096, 16, 4, 0, c4)
+        run(16384, 8, 4, 0, c4)
