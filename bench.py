@@ -289,7 +289,12 @@ def main():
                    "parallelism": "env-shard x%d" % world,
                    "gather": "none" if world == 1 else ("rew/done/info" + ("+obs" if a.gather_obs else ""))},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (E=4096, T=64), from
+                     # the ncu --set full capture summarised in profiles/r1_ww_kernel_final_full.md
+                     "traffic": (1.0890e9 if (E == 4096 and T == 64) else None),
+                     "traffic_unit": "bytes per launch (algorithmic: %d)" % (bpe * E * T),
+                     "peak_kind": peak_kind,
                      "kernel": "ww_kernel<float>", "kernel_ms": kern_ms,
                      "algorithmic_bytes_per_env_step": bpe},
         "gpu_launches": int(launches),
