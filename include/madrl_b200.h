@@ -118,7 +118,7 @@ typedef struct madrl_pursuit_config {
   int32_t n_pursuers, n_evaders;      /* pursuit_evade.py:60-61 (<= 32 / <= 64)                 */
   int32_t xs, ys, n_maps;             /* map_pool shape (n_maps, xs, ys); -1 = building         */
   int32_t obs_range;                  /* pursuit_evade.py:63                                     */
-  int32_t flatten;                    /* pursuit_evade.py:67 (1 only)                            */
+  int32_t flatten;                    /* pursuit_evade.py:67; 0 = conv layout (R, R, 4)          */
   int32_t n_catch, surround;          /* pursuit_evade.py:79,142                                 */
   int32_t reward_global, include_id, sample_maps;
   int32_t max_path_length;            /* VecEnvExecutor horizon, 0 = none                        */
@@ -157,7 +157,8 @@ int madrl_pursuit_set_params(madrl_pursuit* h, double catchr, double constraint_
 /* reset(): obs_dev float [E][Np][obs_dim]. */
 int madrl_pursuit_reset(madrl_pursuit* h, const uint8_t* mask_dev, float* obs_dev, void* stream);
 /* actions_dev int32 [T][E][Np] in {0 left,1 right,2 up,3 down,4 stay} (DiscreteAgent.py:28-38);
- * obs_dev float [T][E][Np][obs_dim]; rew_dev float [T][E][Np] (computed in float64, narrowed once);
+ * obs_dev float [T][E][Np][obs_dim] (obs_dim = 3R^2+id if flatten else 4R^2 laid out [x][y][ch]);
+ * rew_dev float [T][E][Np] (computed in float64, narrowed once);
  * done_dev uint8 [T][E]; info_dev int32 [T][E] = removed. */
 int madrl_pursuit_rollout(madrl_pursuit* h, int T, const int32_t* actions_dev, float* obs_dev,
                           float* rew_dev, uint8_t* done_dev, int32_t* info_dev, int auto_reset,
@@ -214,6 +215,25 @@ int madrl_hostage_reset_host(madrl_hostage* h, const uint8_t* mask_host, void* o
 int madrl_hostage_rollout_host(madrl_hostage* h, int T, const void* actions_host, void* obs_host,
                                void* rew_host, uint8_t* done_host, int32_t* info_host,
                                int auto_reset);
+
+/* ------------------------------------------------------------------ trajectory post-processing
+ * (SURVEY.md 8f rows 2-3).  All tensors are device pointers, float32 unless noted, time-major. */
+/* GAE advantages + discounted returns over paths segmented by `done`
+ * (rllab/rllab/sampler/base.py:48-68).  rew, value, adv, ret: [T][E][A]; done: uint8 [T][E];
+ * last_value [E][A] bootstraps the unfinished tail (NULL = 0, rllab's truncated-path convention). */
+int madrl_gae_f32(int T, int E, int A, const float* rew_dev, const float* value_dev,
+                  const uint8_t* done_dev, const float* last_value_dev, double discount,
+                  double gae_lambda, float* adv_dev, float* ret_dev, void* stream);
+/* ObservationBuffer frame stack (madrl_environments/__init__.py:143-196): obs [T][E][A][D] ->
+ * out [T][E][A][D][B]; carry [E][A][D][B] is the buffer kept between calls; B <= 8. */
+int madrl_frame_stack_f32(int T, int E, int A, int D, int B, const float* obs_dev,
+                          const uint8_t* done_dev, float* carry_dev, float* out_dev, void* stream);
+/* StandardizedEnv running mean / variance normalisation (madrl_environments/__init__.py:241-291),
+ * in place over x [T][n] with float64 state mean/var [n]; center=1 for observations, 0 for rewards
+ * (which are divided by the running std and multiplied by `scale`); enable=0 only applies `scale`. */
+int madrl_standardize_f32(int T, size_t n, float* x_dev, double* mean_dev, double* var_dev,
+                          double alpha, double eps, int center, double scale, int enable,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -102,6 +102,10 @@ def _declare(lib):
     lib.madrl_ww_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
     lib.madrl_ww_reset_host.argtypes = [vp, vp, vp]
     lib.madrl_ww_rollout_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
+    lib.madrl_gae_f32.argtypes = [i32, i32, i32, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp]
+    lib.madrl_frame_stack_f32.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.madrl_standardize_f32.argtypes = [i32, C.c_size_t, vp, vp, vp, C.c_double, C.c_double, i32,
+                                          C.c_double, i32, vp]
     lib.madrl_hostage_state_layout.argtypes = [C.POINTER(HWConfig), C.POINTER(HWLayout)]
     lib.madrl_hostage_create.argtypes = [C.POINTER(HWConfig), vp, C.POINTER(vp)]
     lib.madrl_hostage_destroy.argtypes = [vp]

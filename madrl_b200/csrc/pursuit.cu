@@ -29,7 +29,7 @@ namespace madrl {
 
 struct PEParams {
   int E, env_id_base, Np, Ne, R, off, xs, ys, n_maps, D;
-  int n_catch, surround, reward_global, include_id, sample_maps, max_path_length;
+  int n_catch, surround, reward_global, include_id, sample_maps, max_path_length, flatten;
   int T, mode, auto_reset;
   int smem_per_warp, cells_pad;   // bytes of shared memory per warp; xs*ys rounded up to 32
   double constraint_window, catchr, term_pursuit, urgency;
@@ -310,17 +310,31 @@ __global__ void __launch_bounds__(128, 7) pe_kernel(const __grid_constant__ PEPa
               v1[it] = lds_f32(lut_a + 4u * (c12[it] & 0xffu));         // float32(k) / float32(layer_norm)
               v2[it] = lds_f32(lut_a + 4u * (c12[it] >> 8));
             }
+            if (p.flatten) {
 #pragma unroll
-            for (int it = 0; it < CPL; ++it) {
-              const int w = lane + 32 * it;
-              if (w < RR) {
-                const float v0 = inb[it] ? ((wv[it] & 0xff) ? p.one_val : 0.0f) : p.wall_val;   // pe:433,438
-                store_stream(row + w, v0);
-                store_stream(row + RR + w, v1[it]);
-                store_stream(row + 2 * RR + w, v2[it]);
+              for (int it = 0; it < CPL; ++it) {
+                const int w = lane + 32 * it;
+                if (w < RR) {
+                  const float v0 = inb[it] ? ((wv[it] & 0xff) ? p.one_val : 0.0f) : p.wall_val;   // pe:433,438
+                  store_stream(row + w, v0);
+                  store_stream(row + RR + w, v1[it]);
+                  store_stream(row + 2 * RR + w, v2[it]);
+                }
+              }
+            } else {
+              // flatten=False: np.rollaxis(local_obs[i], 0, 3) -> [x][y][channel], channel 3 holds
+              // i/Np at the window centre and zeros elsewhere (pe:440-449): one 16-byte store per cell
+              const int centre = (R / 2) * R + (R / 2);
+#pragma unroll
+              for (int it = 0; it < CPL; ++it) {
+                const int w = lane + 32 * it;
+                if (w < RR) {
+                  const float v0 = inb[it] ? ((wv[it] & 0xff) ? p.one_val : 0.0f) : p.wall_val;
+                  __stcs(reinterpret_cast<float4*>(row) + w, make_float4(v0, v1[it], v2[it], w == centre ? idval : 0.0f));
+                }
               }
             }
-            if (lane < n_tail) store_stream(row + 3 * RR, idval);                           // pe:444-445
+            if (p.flatten && lane < n_tail) store_stream(row + 3 * RR, idval);              // pe:444-445
           }
         }
         need_reset = false;
@@ -409,7 +423,6 @@ static int pe_validate(const madrl_pursuit_config* c) {
                 "map must be between 2x2 and 4096 cells (<= 255 per side)");
   MADRL_REQUIRE(c->n_maps >= 1, "n_maps must be >= 1");
   MADRL_REQUIRE(c->obs_range >= 1 && c->obs_range * c->obs_range <= 128, "obs_range must be in [1,11]");
-  MADRL_REQUIRE(c->flatten == 1, "only flatten=True observations are implemented in this round");
   MADRL_REQUIRE(c->layer_norm != 0.0, "layer_norm must be non-zero");
   MADRL_REQUIRE(c->constraint_window > 0.0 && c->constraint_window <= 1.0, "constraint_window must be in (0,1]");
   return MADRL_OK;
@@ -434,7 +447,8 @@ extern "C" int madrl_pursuit_state_layout(const madrl_pursuit_config* c, madrl_p
   out->idv = take(4 * 32);
   out->total_bytes = off;
   out->n_agents = (int32_t)Nag;
-  out->obs_dim = (int32_t)(3 * RR + (c->include_id ? 1 : 0));   // pe:108-112
+  out->obs_dim = c->flatten ? (int32_t)(3 * RR + (c->include_id ? 1 : 0))   // pe:108-112
+                            : (int32_t)(4 * RR);                            // (R, R, 4), pe:440-449
   return MADRL_OK;
 }
 
@@ -538,6 +552,7 @@ static int pe_launch(madrl_pursuit* h, int mode, int T, const int32_t* actions, 
   p.xs = c.xs; p.ys = c.ys; p.n_maps = c.n_maps; p.D = h->lay.obs_dim;
   p.n_catch = c.n_catch; p.surround = c.surround; p.reward_global = c.reward_global;
   p.include_id = c.include_id; p.sample_maps = c.sample_maps; p.max_path_length = c.max_path_length;
+  p.flatten = c.flatten;
   p.T = T; p.mode = mode; p.auto_reset = auto_reset;
   const int ncell = c.xs * c.ys, RR = c.obs_range * c.obs_range;
   p.cells_pad = (ncell + 31) / 32 * 32;

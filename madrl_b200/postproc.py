@@ -1,0 +1,128 @@
+"""Device-side consumers of the rollout tensors: what the reference does
+right after ``env.step`` in its sampler loop, as streaming passes over ``[T, E, A, ...]`` tensors.
+
+* ``gae``            rllab ``BaseSampler.process_samples`` (rllab/rllab/sampler/base.py:48-68)
+* ``FrameStack``     ``ObservationBuffer`` (madrl_environments/__init__.py:143-196)
+* ``Standardizer``   ``StandardizedEnv``   (madrl_environments/__init__.py:204-291)
+* ``to_paths``       the per-agent ``paths`` dicts of ``dec_rollout``
+                     (rllab/rllab/sampler/ma_sampler.py:52-100), built on the host from gathered
+                     tensors for callers that still want rllab's list-of-paths format.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def gae(rew, values, done, discount, gae_lambda, last_value=None):
+    """rew, values [T,E,A] float32 cuda; done [T,E] uint8 -> (advantages, returns) [T,E,A].
+
+    Paths end where ``done`` is set (bootstrap 0, base.py:57) and at the end of the rollout
+    (bootstrap ``last_value`` [E,A] if given, else 0)."""
+    rew, values, done = rew.contiguous(), values.contiguous(), done.contiguous()
+    T, E, A = rew.shape
+    adv, ret = torch.empty_like(rew), torch.empty_like(rew)
+    lv = last_value.contiguous() if last_value is not None else None
+    with torch.cuda.device(rew.device):
+        _lib.check(_lib.lib().madrl_gae_f32(T, E, A, _ptr(rew), _ptr(values), _ptr(done), _ptr(lv),
+                                            float(discount), float(gae_lambda), _ptr(adv), _ptr(ret),
+                                            _stream(rew.device)))
+    return adv, ret
+
+
+class FrameStack(object):
+    """ObservationBuffer for a whole env batch: the last ``buffer_size`` observations of every
+    agent stacked on a new minor axis; a reset fills every slot with the reset observation."""
+
+    def __init__(self, n_envs, n_agents, obs_dim, buffer_size, device):
+        self.shape = (n_envs, n_agents, obs_dim, buffer_size)
+        self.carry = torch.zeros(self.shape, dtype=torch.float32, device=device)   # __init__.py:150
+
+    def reset(self, obs0):
+        """obs0 [E,A,D] from engine.reset() -> stacked [E,A,D,B] (__init__.py:186-196)."""
+        self.carry.copy_(obs0.unsqueeze(-1).expand(self.shape))
+        return self.carry.clone()
+
+    def rollout(self, obs, done):
+        """obs [T,E,A,D], done [T,E] from engine.rollout(auto_reset=True) -> [T,E,A,D,B]."""
+        obs, done = obs.contiguous(), done.contiguous()
+        T = obs.shape[0]
+        E, A, D, B = self.shape
+        out = torch.empty((T, E, A, D, B), dtype=torch.float32, device=obs.device)
+        with torch.cuda.device(obs.device):
+            _lib.check(_lib.lib().madrl_frame_stack_f32(T, E, A, D, B, _ptr(obs), _ptr(done),
+                                                        _ptr(self.carry), _ptr(out), _stream(obs.device)))
+        return out
+
+
+class Standardizer(object):
+    """StandardizedEnv's running observation / reward normalisation for a whole env batch
+    (one running estimate per env, agent and observation coordinate, as each reference env keeps
+    its own).  Deviation from the wrapped-single-env reference under auto-reset: the terminal
+    observation of an episode is replaced by the reset observation in the rollout tensor, so the
+    running estimate sees the reset observation only (the reference updates on both)."""
+
+    def __init__(self, n_envs, n_agents, obs_dim, device, scale_reward=1., enable_obsnorm=False,
+                 enable_rewnorm=False, obs_alpha=0.001, rew_alpha=0.001, eps=1e-8):
+        self.scale_reward, self.enable_obsnorm, self.enable_rewnorm = scale_reward, enable_obsnorm, enable_rewnorm
+        self.obs_alpha, self.rew_alpha, self.eps = obs_alpha, rew_alpha, eps
+        self.obs_mean = torch.zeros((n_envs, n_agents, obs_dim), dtype=torch.float64, device=device)
+        self.obs_var = torch.ones((n_envs, n_agents, obs_dim), dtype=torch.float64, device=device)
+        self.rew_mean = torch.zeros((n_envs, n_agents), dtype=torch.float64, device=device)
+        self.rew_var = torch.ones((n_envs, n_agents), dtype=torch.float64, device=device)
+
+    def obs(self, obs):
+        """In place on obs [T,E,A,D] (or [E,A,D])."""
+        if not self.enable_obsnorm:
+            return obs
+        x = obs if obs.dim() == 4 else obs.unsqueeze(0)
+        assert x.is_contiguous()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().madrl_standardize_f32(x.shape[0], self.obs_mean.numel(), _ptr(x),
+                                                        _ptr(self.obs_mean), _ptr(self.obs_var), self.obs_alpha,
+                                                        self.eps, 1, 1.0, 1, _stream(x.device)))
+        return obs
+
+    def rew(self, rew):
+        """In place on rew [T,E,A]: optional running-std division, then scale_reward."""
+        assert rew.is_contiguous()
+        with torch.cuda.device(rew.device):
+            _lib.check(_lib.lib().madrl_standardize_f32(rew.shape[0], self.rew_mean.numel(), _ptr(rew),
+                                                        _ptr(self.rew_mean), _ptr(self.rew_var), self.rew_alpha,
+                                                        self.eps, 0, float(self.scale_reward),
+                                                        int(self.enable_rewnorm), _stream(rew.device)))
+        return rew
+
+
+def to_paths(obs, actions, rew, done, infos=None):
+    """Split time-major rollout arrays [T,E,A,...] (numpy or cpu tensors) into rllab-style paths:
+    one dict per (env, agent, episode) with ``observations/actions/rewards/env_infos`` arrays, the
+    format ``dec_rollout`` returns (ma_sampler.py:88-100).  ``obs[t]`` is the observation the action
+    ``actions[t]`` was taken in, i.e. callers pass obs shifted by one step (reset obs first)."""
+    obs, actions, rew, done = [np.asarray(x) for x in (obs, actions, rew, done)]
+    T, E, A = rew.shape
+    infos = {k: np.asarray(v) for k, v in (infos or {}).items()}
+    paths = []
+    for e in range(E):
+        ends = list(np.nonzero(done[:, e])[0] + 1)
+        if not ends or ends[-1] != T:
+            ends.append(T)
+        start = 0
+        for end in ends:
+            for a in range(A):
+                paths.append(dict(observations=obs[start:end, e, a], actions=actions[start:end, e, a],
+                                  rewards=rew[start:end, e, a],
+                                  env_infos={k: v[start:end, e] for k, v in infos.items()},
+                                  env=e, agent=a, terminated=bool(done[end - 1, e])))
+            start = end
+    return paths

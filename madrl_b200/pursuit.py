@@ -60,7 +60,7 @@ class BatchedPursuitEvade(object):
             mp = mp[None]
         self.map_pool = mp
         self.n_envs, self.n_pursuers, self.n_evaders = n_envs, n_pursuers, n_evaders
-        self.obs_range, self.reward_mech = obs_range, reward_mech
+        self.obs_range, self.reward_mech, self.flatten = obs_range, reward_mech, bool(flatten)
         self.cfg = _lib.PEConfig(
             n_envs=n_envs, env_id_base=env_id_base, n_pursuers=n_pursuers, n_evaders=n_evaders,
             xs=mp.shape[1], ys=mp.shape[2], n_maps=mp.shape[0], obs_range=obs_range,
@@ -252,7 +252,10 @@ class PursuitEvade(AbstractMAEnv, EzPickle):
         self._engine.set_params(self.catchr, self.constraint_window)
         obs = self._engine.reset().cpu().numpy().astype(np.float64)
         self._n_live = self.n_evaders
-        return [obs[0, i] for i in range(self.n_pursuers)]
+        return [self._shape(obs[0, i]) for i in range(self.n_pursuers)]
+
+    def _shape(self, o):
+        return o if self.flatten else o.reshape(self.obs_range, self.obs_range, 4)
 
     @property
     def is_terminal(self):
@@ -268,7 +271,7 @@ class PursuitEvade(AbstractMAEnv, EzPickle):
         rew = rew[0].cpu().numpy().astype(np.float64)
         removed = int(info['removed'][0].item())
         self._n_live -= removed
-        obslist = [obs[0, i] for i in range(self.n_pursuers)]
+        obslist = [self._shape(obs[0, i]) for i in range(self.n_pursuers)]
         if self._reward_mech == 'global':
             return obslist, [rew[0]] * self.n_pursuers, bool(done[0].item()), {'removed': removed}
         return obslist, rew, bool(done[0].item()), {'removed': removed}

@@ -1,0 +1,85 @@
+"""CPU oracles (TEST INFRASTRUCTURE) for the trajectory post-processing passes: restatements of
+
+* rllab ``BaseSampler.process_samples`` advantage / return computation
+  (rllab/rllab/sampler/base.py:48-68; ``discount_cumsum`` = rllab/rllab/misc/special.py:107-111),
+* ``ObservationBuffer`` (madrl_environments/__init__.py:143-196),
+* ``StandardizedEnv``   (madrl_environments/__init__.py:204-291),
+
+applied to time-major rollout arrays of ONE env ``[T, A, ...]`` with VecEnvExecutor auto-reset
+semantics (the obs slot of a done step already holds the reset observation).
+"""
+import numpy as np
+import scipy.signal
+
+
+def discount_cumsum(x, discount):                      # special.py:107-111
+    return scipy.signal.lfilter([1], [1, float(-discount)], x[::-1], axis=0)[::-1]
+
+
+def gae_env(rew, val, done, discount, gae_lambda, last_value=None):
+    """rew, val [T, A]; done [T] -> adv, ret [T, A] (float64)."""
+    T, A = rew.shape
+    adv, ret = np.zeros((T, A)), np.zeros((T, A))
+    ends = list(np.nonzero(done)[0] + 1)
+    tail_open = not ends or ends[-1] != T
+    if tail_open:
+        ends.append(T)
+    start = 0
+    for n, end in enumerate(ends):
+        boot = np.zeros(A)
+        if tail_open and n == len(ends) - 1 and last_value is not None:
+            boot = np.asarray(last_value, dtype=np.float64)
+        for a in range(A):
+            r = rew[start:end, a].astype(np.float64)
+            b = np.append(val[start:end, a].astype(np.float64), boot[a])          # base.py:57
+            deltas = r + discount * b[1:] - b[:-1]                                # base.py:58-60
+            adv[start:end, a] = discount_cumsum(deltas, discount * gae_lambda)    # base.py:61-62
+            # returns bootstrap the same way when a tail value is supplied
+            ret[start:end, a] = discount_cumsum(np.append(r, boot[a]), discount)[:-1] \
+                if boot[a] != 0 else discount_cumsum(r, discount)                 # base.py:63
+        start = end
+    return adv, ret
+
+
+def frame_stack_env(obs0, obs, done, B):
+    """obs0 [A, D] reset obs; obs [T, A, D]; done [T] -> (stack0 [A,D,B], stacked [T,A,D,B])."""
+    A, D = obs0.shape
+    buf = np.zeros((A, D, B))
+    for b in range(B):                                  # reset(): __init__.py:186-196
+        buf[..., b] = obs0
+    out0 = buf.copy()
+    out = np.zeros((obs.shape[0], A, D, B))
+    for t in range(obs.shape[0]):
+        if done[t]:                                     # executor called wrapper.reset()
+            for b in range(B):
+                buf[..., b] = obs[t]
+        else:                                           # step(): __init__.py:176-183
+            buf[..., 0:B - 1] = buf[..., 1:B].copy()
+            buf[..., -1] = obs[t]
+        out[t] = buf
+    return out0, out
+
+
+class StandardizeEnv(object):
+    """Running estimates of one env (one per agent, __init__.py:221-234)."""
+
+    def __init__(self, A, D, scale_reward=1., enable_obsnorm=False, enable_rewnorm=False,
+                 obs_alpha=0.001, rew_alpha=0.001, eps=1e-8):
+        self.scale_reward, self.eo, self.er = scale_reward, enable_obsnorm, enable_rewnorm
+        self.oa, self.ra, self.eps = obs_alpha, rew_alpha, eps
+        self.obs_mean, self.obs_var = np.zeros((A, D)), np.ones((A, D))
+        self.rew_mean, self.rew_var = np.zeros(A), np.ones(A)
+
+    def obs(self, x):                                   # standardize_obs, __init__.py:258-262
+        if not self.eo:
+            return x
+        self.obs_mean = (1 - self.oa) * self.obs_mean + self.oa * x
+        self.obs_var = (1 - self.oa) * self.obs_var + self.oa * np.square(x - self.obs_mean)
+        return (x - self.obs_mean) / (np.sqrt(self.obs_var) + self.eps)
+
+    def rew(self, r):                                   # standardize_rew + scale, __init__.py:264-289
+        if self.er:
+            self.rew_mean = (1 - self.ra) * self.rew_mean + self.ra * r
+            self.rew_var = (1 - self.ra) * self.rew_var + self.ra * np.square(r - self.rew_mean)
+            r = r / (np.sqrt(self.rew_var) + self.eps)
+        return self.scale_reward * r

@@ -1,0 +1,141 @@
+"""Post-processing passes: oracle vs the REAL reference wrappers (CPU, needs /root/reference) and
+CUDA kernels vs oracle (GPU)."""
+import numpy as np
+import pytest
+
+from oracle.postproc_oracle import StandardizeEnv, discount_cumsum, frame_stack_env, gae_env
+
+
+class ScriptedEnv(object):
+    """Minimal AbstractMAEnv stand-in that replays given observations / rewards."""
+
+    def __init__(self, obs0, obs, rew, spaces_mod):
+        self.obs0, self.obs_seq, self.rew_seq, self.t = obs0, obs, rew, 0
+        A, D = obs0.shape
+
+        class Ag(object):
+            observation_space = spaces_mod.Box(low=-10, high=10, shape=(D,))
+            action_space = spaces_mod.Box(low=-1, high=1, shape=(2,))
+        self.agents = [Ag() for _ in range(A)]
+        self.reward_mech = 'local'
+
+    def seed(self, s=None):
+        return [s]
+
+    def reset(self):
+        return [o.copy() for o in self.obs0]
+
+    def step(self, a):
+        o, r = self.obs_seq[self.t], self.rew_seq[self.t]
+        self.t += 1
+        return [x.copy() for x in o], list(r), False, {}
+
+
+@pytest.mark.reference
+def test_oracles_equal_reference_wrappers():
+    from oracle.refshim import install
+    install()
+    import gym.spaces as spaces
+    import madrl_environments as me
+    me.ent = None  # noqa  (ObservationBuffer.agents has a typo'd name; not used here)
+    rs = np.random.RandomState(0)
+    T, A, D, B = 40, 3, 5, 4
+    obs0, obs, rew = rs.randn(A, D), rs.randn(T, A, D), rs.randn(T, A)
+    # ObservationBuffer
+    w = me.ObservationBuffer.__new__(me.ObservationBuffer)
+    w._unwrapped = ScriptedEnv(obs0, obs, rew, spaces)
+    w._buffer_size = B
+    w._buffer = [np.zeros((D, B)) for _ in range(A)]
+    out0 = np.array(w.reset())
+    ref = np.array([np.array(w.step(None)[0]) for _ in range(T)])
+    o0, o = frame_stack_env(obs0, obs, np.zeros(T, bool), B)
+    assert np.array_equal(out0, o0) and np.array_equal(ref, o)
+    # StandardizedEnv
+    env = ScriptedEnv(obs0, obs, rew, spaces)
+    s = me.StandardizedEnv(env, scale_reward=0.5, enable_obsnorm=True, enable_rewnorm=True,
+                           obs_alpha=0.05, rew_alpha=0.02)
+    mine = StandardizeEnv(A, D, 0.5, True, True, 0.05, 0.02)
+    assert np.array_equal(np.array(s.reset()), mine.obs(obs0))
+    for t in range(T):
+        so, sr, _, _ = s.step(None)
+        assert np.array_equal(np.array(so), mine.obs(obs[t]))
+        assert np.array_equal(np.array(sr), mine.rew(rew[t]))
+
+
+def test_gae_oracle_matches_rllab_formulas():
+    rs = np.random.RandomState(1)
+    T, A = 30, 2
+    rew, val = rs.randn(T, A), rs.randn(T, A)
+    done = np.zeros(T, bool)
+    done[[9, 19, 29]] = True
+    adv, ret = gae_env(rew, val, done, 0.99, 0.95)
+    for s, e in ((0, 10), (10, 20), (20, 30)):            # rllab: one call per complete path
+        for a in range(A):
+            b = np.append(val[s:e, a], 0)
+            deltas = rew[s:e, a] + 0.99 * b[1:] - b[:-1]
+            assert np.array_equal(adv[s:e, a], discount_cumsum(deltas, 0.99 * 0.95))
+            assert np.array_equal(ret[s:e, a], discount_cumsum(rew[s:e, a], 0.99))
+    assert ret[9, 0] == rew[9, 0]                          # a path's last step sees no future
+
+
+def test_to_paths_splits_at_done():
+    from madrl_b200.postproc import to_paths
+    T, E, A = 6, 2, 2
+    done = np.zeros((T, E), np.uint8)
+    done[2, 0] = 1
+    done[5, 1] = 1
+    rew = np.arange(T * E * A, dtype=np.float32).reshape(T, E, A)
+    paths = to_paths(np.zeros((T, E, A, 3)), np.zeros((T, E, A, 2)), rew, done, dict(x=np.ones((T, E))))
+    lens = sorted((p['env'], p['agent'], len(p['rewards']), p['terminated']) for p in paths)
+    assert lens == [(0, 0, 3, False), (0, 0, 3, True), (0, 1, 3, False), (0, 1, 3, True),
+                    (1, 0, 6, True), (1, 1, 6, True)]
+    assert all(p['env_infos']['x'].shape[0] == len(p['rewards']) for p in paths)
+
+
+@pytest.mark.gpu
+def test_cuda_postproc_matches_oracle():
+    import torch
+    from madrl_b200.postproc import FrameStack, Standardizer, gae
+    rs = np.random.RandomState(2)
+    T, E, A, D, B = 50, 7, 3, 11, 4
+    obs0 = rs.randn(E, A, D).astype(np.float32)
+    obs = rs.randn(T, E, A, D).astype(np.float32)
+    rew = rs.randn(T, E, A).astype(np.float32)
+    val = rs.randn(T, E, A).astype(np.float32)
+    last = rs.randn(E, A).astype(np.float32)
+    done = (rs.rand(T, E) < 0.1)
+    dev = 'cuda'
+    d_t = torch.as_tensor(done.astype(np.uint8), device=dev)
+    # GAE
+    for lv in (None, last):
+        adv, ret = gae(torch.as_tensor(rew, device=dev), torch.as_tensor(val, device=dev), d_t, 0.99, 0.95,
+                       None if lv is None else torch.as_tensor(lv, device=dev))
+        for e in range(E):
+            a_o, r_o = gae_env(rew[:, e], val[:, e], done[:, e], 0.99, 0.95, None if lv is None else lv[e])
+            assert np.abs(adv[:, e].cpu().numpy() - a_o).max() < 1e-4
+            assert np.abs(ret[:, e].cpu().numpy() - r_o).max() < 1e-4
+    # frame stack (two consecutive rollouts exercise the carry)
+    fs = FrameStack(E, A, D, B, dev)
+    st0 = fs.reset(torch.as_tensor(obs0, device=dev)).cpu().numpy()
+    o1 = fs.rollout(torch.as_tensor(obs[:20], device=dev), d_t[:20]).cpu().numpy()
+    o2 = fs.rollout(torch.as_tensor(obs[20:], device=dev), d_t[20:]).cpu().numpy()
+    for e in range(E):
+        s0, so = frame_stack_env(obs0[e].astype(np.float64), obs[:, e].astype(np.float64), done[:, e], B)
+        assert np.array_equal(st0[e], s0.astype(np.float32))
+        assert np.array_equal(np.concatenate([o1, o2])[:, e], so.astype(np.float32))
+    # standardizer
+    sd = Standardizer(E, A, D, dev, scale_reward=0.5, enable_obsnorm=True, enable_rewnorm=True,
+                      obs_alpha=0.05, rew_alpha=0.02)
+    x0 = torch.as_tensor(obs0, device=dev).clone()
+    sd.obs(x0)
+    xo = torch.as_tensor(obs, device=dev).clone()
+    xr = torch.as_tensor(rew, device=dev).clone()
+    sd.obs(xo)
+    sd.rew(xr)
+    for e in range(E):
+        m = StandardizeEnv(A, D, 0.5, True, True, 0.05, 0.02)
+        assert np.abs(m.obs(obs0[e].astype(np.float64)) - x0[e].cpu().numpy()).max() < 1e-5
+        for t in range(T):
+            assert np.abs(m.obs(obs[t, e].astype(np.float64)) - xo[t, e].cpu().numpy()).max() < 1e-5
+            assert np.abs(m.rew(rew[t, e].astype(np.float64)) - xr[t, e].cpu().numpy()).max() < 1e-5
+        assert np.abs(m.obs_var - sd.obs_var[e].cpu().numpy()).max() < 1e-12

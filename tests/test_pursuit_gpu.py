@@ -48,6 +48,9 @@ CASES = {
                               catchr=0.1, term_pursuit=5.0)),
     "even_range": (small_map, dict(n_evaders=3, n_pursuers=3, obs_range=4, surround=False, n_catch=1,
                                    reward_mech='global')),
+    "conv_layout": (pool16, dict(C3, flatten=False, n_evaders=12, obs_range=5)),     # (R, R, 4) obs
+    "conv_small": (small_map, dict(n_evaders=3, n_pursuers=3, obs_range=4, surround=False, n_catch=1,
+                                   reward_mech='global', flatten=False)),
 }
 
 
@@ -72,7 +75,8 @@ def check_state(eng, oracles):
 
 @pytest.mark.parametrize("name,E,T", [("c3", 24, 120), ("c3_global", 8, 80), ("ncatch", 16, 120),
                                       ("window_r9", 16, 120), ("many_evaders", 4, 40),
-                                      ("crowd", 48, 300), ("even_range", 32, 150)])
+                                      ("crowd", 48, 300), ("even_range", 32, 150),
+                                      ("conv_layout", 12, 100), ("conv_small", 16, 150)])
 def test_trajectories_bit_exact(name, E, T):
     mk, cfg = CASES[name]
     maps = mk()
@@ -81,7 +85,7 @@ def test_trajectories_bit_exact(name, E, T):
     obs0 = eng.reset().cpu().numpy()
     oracles = [PursuitOracle(maps, rng=Stream(seed, base + e), **cfg) for e in range(E)]
     for e, o in enumerate(oracles):
-        assert np.array_equal(f32(o.reset()), obs0[e]), e
+        assert np.array_equal(f32(o.reset()).reshape(obs0[e].shape), obs0[e]), e
     check_state(eng, oracles)
     Np = cfg['n_pursuers']
     act = np.random.RandomState(9).randint(0, 5, size=(T, E, Np)).astype(np.int32)
@@ -91,7 +95,7 @@ def test_trajectories_bit_exact(name, E, T):
         for e, o in enumerate(oracles):
             oo, rr, dd, ii = o.step(act[t, e])
             assert ii['removed'] == removed[t, e] and dd == bool(done[t, e]), (t, e)
-            assert np.array_equal(f32(oo), obs[t, e]), (t, e)
+            assert np.array_equal(f32(oo).reshape(obs[t, e].shape), obs[t, e]), (t, e)
             assert np.array_equal(f32(rr), rew[t, e]), (t, e, rr, rew[t, e])
             total_removed += ii['removed']
     check_state(eng, oracles)
