@@ -174,25 +174,25 @@ def main():
     # synthetic actions 0.5*N(0,1) (waterworld.py:486), a different tensor per timed step
     n_act = min(a.steps, 4)
     actions = [torch.randn(T, E, Np, 2, device=dev, generator=g) * 0.5 for _ in range(n_act)]
-    out = (torch.empty((T, E, Np, D), device=dev), torch.empty((T, E, Np), device=dev),
-           torch.empty((T, E), dtype=torch.uint8, device=dev),
-           torch.empty((T, E, 2), dtype=torch.int32, device=dev))
-    if world > 1:
-        def gbuf(x):   # all_gather_into_tensor output: ranks concatenated along dim 0
-            return torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)
-        g_rew, g_done, g_info = gbuf(out[1]), gbuf(out[2]), gbuf(out[3])
-        g_obs = gbuf(out[0]) if a.gather_obs else None
+    from madrl_b200.dist import PackedTrajectory
+    # rewards / dones / infos of a rollout live in ONE contiguous buffer -> a single collective
+    packed = PackedTrajectory(T, E, Np, 2, dev)
+    out = (torch.empty((T, E, Np, D), device=dev), packed.rew, packed.done, packed.info)
+    g_obs = None
+    if world > 1 and a.gather_obs:
+        g_obs = torch.empty((world * T, E, Np, D), device=dev)
+
+    def exchange():
+        # the ONE per-rollout gather of trajectory tensors over NVLink (rewards / dones / infos;
+        # obs stays sharded with the data-parallel learner unless --gather-obs)
+        if world > 1:
+            packed.gather_raw()
+            if a.gather_obs:
+                dist.all_gather_into_tensor(g_obs, out[0])
 
     def one_step(i):
         eng.rollout(actions[i % n_act], auto_reset=True, out=out)
-        if world > 1:
-            # the per-rollout gather of trajectory tensors over NVLink (rewards / dones / infos;
-            # obs stays sharded with the data-parallel learner unless --gather-obs)
-            dist.all_gather_into_tensor(g_rew, out[1])
-            dist.all_gather_into_tensor(g_done, out[2])
-            dist.all_gather_into_tensor(g_info, out[3])
-            if a.gather_obs:
-                dist.all_gather_into_tensor(g_obs, out[0])
+        exchange()
 
     def barrier():
         if world > 1:
@@ -214,12 +214,7 @@ def main():
         kev[i][0].record()
         eng.rollout(actions[i % n_act], auto_reset=True, out=out)
         kev[i][1].record()
-        if world > 1:
-            dist.all_gather_into_tensor(g_rew, out[1])
-            dist.all_gather_into_tensor(g_done, out[2])
-            dist.all_gather_into_tensor(g_info, out[3])
-            if a.gather_obs:
-                dist.all_gather_into_tensor(g_obs, out[0])
+        exchange()
     ev1.record()
     barrier()
     launches = launch_count() - l0
@@ -287,7 +282,8 @@ def main():
                    "envs_per_gpu": E, "t_inner": T, "actions": "0.5*N(0,1), HBM-resident",
                    "l2": "outputs per launch (%.0f MB) exceed L2" % (out[0].numel() * 4 / 1e6),
                    "parallelism": "env-shard x%d" % world,
-                   "gather": "none" if world == 1 else ("rew/done/info" + ("+obs" if a.gather_obs else ""))},
+                   "gather": "none" if world == 1 else ("one packed all_gather of rew/done/info per rollout" +
+                                                        (" + obs all_gather" if a.gather_obs else ""))},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (E=4096, T=64), from

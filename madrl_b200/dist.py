@@ -77,3 +77,49 @@ def gather_trajectories(tensors, env_dim=1, group=None, dst=None, equal_shards=T
             parts = [c.narrow(env_dim, 0, sz) for c, sz in zip(buf.view([world] + shp).unbind(0), sizes)]
         out.append(torch.cat(parts, dim=env_dim) if parts is not None else None)
     return tuple(out)
+
+
+class PackedTrajectory(object):
+    """Reward / done / info tensors of one rollout carved out of ONE contiguous byte buffer, so the
+    per-rollout exchange is a single collective (`gather()`), not one per tensor.  The env kernels
+    write straight into the views."""
+
+    def __init__(self, T, n_envs, n_agents, info_width, device, rew_dtype=torch.float32):
+        esz = torch.empty((), dtype=rew_dtype).element_size()
+        self.shapes = dict(rew=(T, n_envs, n_agents), info=(T, n_envs, info_width) if info_width > 1 else (T, n_envs),
+                           done=(T, n_envs))
+        r_b = T * n_envs * n_agents * esz
+        i_b = T * n_envs * info_width * 4
+        d_b = T * n_envs
+        self.nbytes = (r_b + i_b + d_b + 15) // 16 * 16
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.rew = self.buf[:r_b].view(rew_dtype).view(self.shapes['rew'])
+        self.info = self.buf[r_b:r_b + i_b].view(torch.int32).view(self.shapes['info'])
+        self.done = self.buf[r_b + i_b:r_b + i_b + d_b].view(self.shapes['done'])
+        self._r_b, self._i_b, self._d_b, self._rew_dtype = r_b, i_b, d_b, rew_dtype
+        self._gbuf = None
+
+    def gather(self, group=None):
+        """ONE all_gather of the packed buffer; returns (rew, done, info) with a leading rank axis
+        ([W, T, E_local, ...] views, no copies)."""
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return self.rew.unsqueeze(0), self.done.unsqueeze(0), self.info.unsqueeze(0)
+        world = dist.get_world_size(group)
+        if self._gbuf is None:
+            self._gbuf = torch.empty(world * self.nbytes, dtype=torch.uint8, device=self.buf.device)
+        dist.all_gather_into_tensor(self._gbuf, self.buf, group=group)
+        g = self._gbuf.view(world, self.nbytes)
+        r_b, i_b, d_b = self._r_b, self._i_b, self._d_b
+        rew = torch.stack([g[w, :r_b].view(self._rew_dtype).view(self.shapes['rew']) for w in range(world)])
+        info = torch.stack([g[w, r_b:r_b + i_b].view(torch.int32).view(self.shapes['info']) for w in range(world)])
+        done = torch.stack([g[w, r_b + i_b:r_b + i_b + d_b].view(self.shapes['done']) for w in range(world)])
+        return rew, done, info
+
+    def gather_raw(self, group=None):
+        """The collective only (no unpacking): what sits in the benchmark's timed region."""
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            world = dist.get_world_size(group)
+            if self._gbuf is None:
+                self._gbuf = torch.empty(world * self.nbytes, dtype=torch.uint8, device=self.buf.device)
+            dist.all_gather_into_tensor(self._gbuf, self.buf, group=group)
+        return self._gbuf

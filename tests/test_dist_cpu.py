@@ -43,6 +43,16 @@ def _worker(rank, world, port, ragged, q):
         obs, rew = rollout_oracle(lo, hi)
         g_obs, g_rew = gather_trajectories((obs, rew), env_dim=1, equal_shards=not ragged)
         d_obs, = gather_trajectories((obs,), env_dim=1, dst=0) if not ragged else (g_obs,)
+        if not ragged:     # the single-collective packed exchange used by bench.py
+            from madrl_b200.dist import PackedTrajectory
+            pk = PackedTrajectory(T, hi - lo, NP, 2, "cpu")
+            pk.rew.copy_(rew)
+            pk.done.fill_(rank)
+            pk.info.fill_(7 + rank)
+            p_rew, p_done, p_info = pk.gather()
+            assert torch.equal(torch.cat(list(p_rew), dim=1), g_rew)
+            assert [int(p_done[w].max()) for w in range(world)] == list(range(world))
+            assert [int(p_info[w].min()) for w in range(world)] == [7 + w for w in range(world)]
         if rank == 0:
             f_obs, f_rew = rollout_oracle(0, E_GLOBAL)
             ok = torch.equal(g_obs, f_obs) and torch.equal(g_rew, f_rew) and torch.equal(d_obs, f_obs)
