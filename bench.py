@@ -113,7 +113,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (weak scaling)")
-    ap.add_argument("--t-inner", type=int, default=64, help="lockstep env steps per rollout launch")
+    ap.add_argument("--t-inner", type=int, default=256, help="lockstep env steps per rollout launch")
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -286,9 +286,10 @@ def main():
                                                         (" + obs all_gather" if a.gather_obs else ""))},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (E=4096, T=64), from
-                     # the ncu --set full capture summarised in profiles/r1_ww_kernel_final_full.md
-                     "traffic": (1.0890e9 if (E == 4096 and T == 64) else None),
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch: 1.0890 GB measured for
+                     # one E=4096, T=64 launch (ncu --set full, profiles/r1_ww_kernel_final_full.md),
+                     # i.e. 17.0 MB per lockstep step, scaled to this launch's T
+                     "traffic": (1.0890e9 / 64 * T if E == 4096 else None),
                      "traffic_unit": "bytes per launch (algorithmic: %d)" % (bpe * E * T),
                      "peak_kind": peak_kind,
                      "kernel": "ww_kernel<float>", "kernel_ms": kern_ms,
