@@ -26,6 +26,70 @@ WW_CFG = dict(n_pursuers=5, n_evaders=5, n_poison=10, n_sensors=30)   # class de
 METRIC = "agent_env_steps_per_sec"
 UNIT = "agent-env-steps/s"
 
+PE_C3 = dict(n_evaders=30, n_pursuers=8, obs_range=7, surround=True, n_catch=2, flatten=True,
+             reward_mech='local', catchr=0.1, term_pursuit=5.0, sample_maps=True, include_id=True)
+HW_C5 = (10, 16, 16, 4, 2)
+
+# name -> description of the BASELINE.json config it measures (default = configs[1])
+WORKLOADS = {
+    "waterworld": dict(desc="MAWaterWorld 5p/5e/10po/30 sensors", envs=4096, agents=5, family="ww", cfg=WW_CFG),
+    "waterworld_c4": dict(desc="MAWaterWorld 20p/50e/50po/30 sensors", envs=4096, agents=20, family="ww",
+                          cfg=dict(n_pursuers=20, n_evaders=50, n_poison=50, n_sensors=30)),
+    "pursuit": dict(desc="PursuitEvade 16x16 map_pool16, 8p/30e, obs_range 7, surround", envs=65536, agents=8,
+                    family="pe", cfg=PE_C3),
+    "hostage": dict(desc="ContinuousHostageWorld 10 rescuers/16 hostages/16 criminals/30 sensors", envs=8192,
+                    agents=10, family="hw", cfg=HW_C5),
+}
+
+
+def bytes_per_env_step(wl):
+    """Algorithmic (compulsory) bytes per env-step, SURVEY.md 8(d)."""
+    w = WORKLOADS[wl]
+    if w["family"] == "ww":
+        c = w["cfg"]
+        return ww_bytes_per_env_step(c["n_pursuers"], c["n_evaders"], c["n_poison"], c["n_sensors"])
+    if w["family"] == "pe":
+        Np, Ne, R = 8, 30, 7
+        return 2 * (2 * Np + 2 * Ne + (Ne + 7) // 8 + 1 + 8) + 4 * Np + 4 * Np * (3 * R * R + 1) + 4 * Np + 1 + 4
+    Nr, Nh, Nc, K = 10, 16, 16, 30
+    return 4 * (2 * 4 * Nr + 2 * 4 * Nc + 2 * Nh + 4) + 2 * ((Nh + 7) // 8 + 12 + 8) + 4 * 2 * Nr + \
+        4 * Nr * (5 * K + 6) + 4 * Nr + 9
+
+
+def make_engine(wl, E, dev, rank, mpl=0):
+    from madrl_b200 import BatchedHostageWorld, BatchedMAWaterWorld, BatchedPursuitEvade
+    w = WORKLOADS[wl]
+    if w["family"] == "ww":
+        return BatchedMAWaterWorld(E, device=dev, seed=0, env_id_base=rank * E, **w["cfg"])
+    if w["family"] == "pe":
+        maps = np.load(os.path.join(ROOT, "maps", "map_pool16.npy"))
+        return BatchedPursuitEvade(E, maps, device=dev, seed=0, env_id_base=rank * E, max_path_length=500, **w["cfg"])
+    return BatchedHostageWorld(E, *w["cfg"], device=dev, seed=0, env_id_base=rank * E)
+
+
+def make_actions(wl, T, E, dev, g, host=False):
+    import torch
+    w = WORKLOADS[wl]
+    d = "cpu" if host else dev
+    gg = None if host else g
+    if w["family"] == "pe":
+        return torch.randint(0, 5, (T, E, w["agents"]), dtype=torch.int32, device=d, generator=gg)
+    return torch.randn(T, E, w["agents"], 2, device=d, generator=gg) * 0.5
+
+
+def make_oracle(wl, seed):
+    from oracle.philox import Stream
+    w = WORKLOADS[wl]
+    if w["family"] == "ww":
+        from oracle.waterworld_oracle import WaterworldOracle
+        return WaterworldOracle(rng=Stream(seed, seed), **w["cfg"])
+    if w["family"] == "pe":
+        from oracle.pursuit_oracle import PursuitOracle
+        maps = np.load(os.path.join(ROOT, "maps", "map_pool16.npy"))
+        return PursuitOracle(maps, rng=Stream(seed, seed), **w["cfg"])
+    from oracle.hostage_oracle import HostageOracle
+    return HostageOracle(*w["cfg"], rng=Stream(seed, seed))
+
 
 def ww_bytes_per_env_step(Np, Ne, Npo, K):
     """Algorithmic (compulsory) bytes per env-step, SURVEY.md 8(d) / BASELINE.md section 5."""
@@ -76,33 +140,36 @@ class ClockSampler(threading.Thread):
 
 # ----------------------------------------------------------------------------- CPU baseline
 def _cpu_worker(args):
-    seconds, seed = args
-    from oracle.philox import Stream
-    from oracle.waterworld_oracle import WaterworldOracle
-    env = WaterworldOracle(rng=Stream(seed, seed), **WW_CFG)
+    seconds, seed, wl = args
+    w = WORKLOADS[wl]
+    env = make_oracle(wl, seed)
     env.reset()
     rs = np.random.RandomState(seed)
-    acts = rs.randn(4096, WW_CFG['n_pursuers'] * 2) * 0.5
+    if w["family"] == "pe":
+        acts = rs.randint(0, 5, size=(4096, w["agents"]))
+    else:
+        acts = rs.randn(4096, w["agents"] * 2) * 0.5
     for i in range(50):
         env.step(acts[i])
-    n, t0 = 0, time.perf_counter()
+    n, last_reset, t0 = 0, 0, time.perf_counter()
     while time.perf_counter() - t0 < seconds:
         _, _, done, _ = env.step(acts[n % 4096])
-        if done:
-            env.reset()
         n += 1
+        if done or n - last_reset >= 500:
+            env.reset()
+            last_reset = n
     return n, time.perf_counter() - t0
 
 
-def cpu_baseline(seconds, procs):
+def cpu_baseline(seconds, procs, wl="waterworld"):
     """The CPU path (float64 NumPy oracle port of the reference step(), one env per process the
     way rllab's StatefulPool parallelises; rllab/rllab/sampler/stateful_pool.py:102-157)."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     with ctx.Pool(procs) as pool:
-        res = pool.map(_cpu_worker, [(seconds, 100 + i) for i in range(procs)])
+        res = pool.map(_cpu_worker, [(seconds, 100 + i, wl) for i in range(procs)])
     env_steps_per_s = sum(n / dt for n, dt in res)
-    return env_steps_per_s * WW_CFG['n_pursuers']
+    return env_steps_per_s * WORKLOADS[wl]["agents"]
 
 
 # ----------------------------------------------------------------------------- main
@@ -112,8 +179,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (weak scaling)")
-    ap.add_argument("--t-inner", type=int, default=256, help="lockstep env steps per rollout launch")
+    ap.add_argument("--workload", default="waterworld", choices=sorted(WORKLOADS),
+                    help="default = BASELINE.json configs[1]; the others are the remaining configs")
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (weak scaling); 0 = the config's")
+    ap.add_argument("--t-inner", type=int, default=0, help="lockstep env steps per rollout launch (0 = auto)")
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -126,7 +195,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    Np = WW_CFG['n_pursuers']
+    WL = WORKLOADS[a.workload]
+    Np = WL["agents"]
+    if a.envs <= 0:
+        a.envs = WL["envs"]
+    if a.t_inner <= 0:      # keep one launch's obs output around 4.5 GB
+        a.t_inner = 256 if a.workload == "waterworld" else (16 if a.workload == "pursuit" else 64)
     host_cores = os.cpu_count() or 1
 
     if a.impl == "reference":
@@ -135,9 +209,9 @@ def main():
         procs = host_cores
         per = max(2.0, min(10.0, 60.0 / max(1, a.steps + a.warmup)))
         for _ in range(a.warmup):
-            cpu_baseline(0.5, procs)
+            cpu_baseline(0.5, procs, a.workload)
         t0 = time.perf_counter()
-        vals = [cpu_baseline(per, procs) for _ in range(a.steps)]
+        vals = [cpu_baseline(per, procs, a.workload) for _ in range(a.steps)]
         dt = time.perf_counter() - t0
         v = float(np.mean(vals))
         print(json.dumps({
@@ -145,26 +219,25 @@ def main():
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "MAWaterWorld 5p/5e/10po/30 sensors, one env per host process",
-                       "envs_per_gpu": a.envs},
+            "config": {"workload": WL["desc"] + ", one env per host process", "envs_per_gpu": a.envs},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
                              "sample": "%d processes x %.1f s of step() per bench step, float64 NumPy "
-                                       "oracle port of waterworld.py (the reference tree cannot travel "
-                                       "to the GPU box)" % (procs, per)},
+                                       "oracle port of the reference step() (the reference tree cannot "
+                                       "travel to the GPU box)" % (procs, per)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
 
     import torch
     import torch.distributed as dist
-    from madrl_b200 import BatchedMAWaterWorld, launch_count
+    from madrl_b200 import launch_count
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     E, T = a.envs, a.t_inner
-    eng = BatchedMAWaterWorld(E, device=dev, seed=0, env_id_base=rank * E, **WW_CFG)
+    eng = make_engine(a.workload, E, dev, rank)
     if a.wpb or a.bps:
         eng.set_launch(a.wpb, a.bps)
     D = eng.obs_dim
@@ -173,10 +246,11 @@ def main():
     g.manual_seed(1234 + rank)
     # synthetic actions 0.5*N(0,1) (waterworld.py:486), a different tensor per timed step
     n_act = min(a.steps, 4)
-    actions = [torch.randn(T, E, Np, 2, device=dev, generator=g) * 0.5 for _ in range(n_act)]
+    actions = [make_actions(a.workload, T, E, dev, g) for _ in range(n_act)]
     from madrl_b200.dist import PackedTrajectory
     # rewards / dones / infos of a rollout live in ONE contiguous buffer -> a single collective
-    packed = PackedTrajectory(T, E, Np, 2, dev)
+    info_w = 1 if WL["family"] == "pe" else 2
+    packed = PackedTrajectory(T, E, Np, info_w, dev)
     out = (torch.empty((T, E, Np, D), device=dev), packed.rew, packed.done, packed.info)
     g_obs = None
     if world > 1 and a.gather_obs:
@@ -245,10 +319,11 @@ def main():
     e2e = None
     if not a.no_e2e:
         Te = min(T, 16)
-        h_act = [torch.randn(Te, E, Np, 2).mul_(0.5).pin_memory() for _ in range(2)]
+        Te = min(Te, max(1, (1 << 28) // (E * Np * D * 4)))      # <= 256 MB of obs per call
+        h_act = [make_actions(a.workload, Te, E, dev, g, host=True).pin_memory() for _ in range(2)]
         h_out = (torch.empty((Te, E, Np, D)).pin_memory(), torch.empty((Te, E, Np)).pin_memory(),
                  torch.empty((Te, E), dtype=torch.uint8).pin_memory(),
-                 torch.empty((Te, E, 2), dtype=torch.int32).pin_memory())
+                 torch.empty((Te, E, 2) if info_w == 2 else (Te, E), dtype=torch.int32).pin_memory())
         for i in range(2):
             eng.rollout_host(h_act[i % 2], *h_out)
         barrier()
@@ -262,24 +337,26 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": world * E * Np * Te * n_e2e / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(h_act[0].numel() * 4),
+               "h2d_bytes_per_step": int(h_act[0].numel() * h_act[0].element_size()),
                "d2h_bytes_per_step": int(sum(x.numel() * x.element_size() for x in h_out)),
-               "t_inner": Te, "api": "madrl_ww_rollout_host (pinned host buffers)"}
+               "t_inner": Te, "api": "madrl_%s_rollout_host (pinned host buffers)" % {"ww": "ww", "pe": "pursuit", "hw": "hostage"}[WL["family"]]}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    bpe = ww_bytes_per_env_step(Np, WW_CFG['n_evaders'], WW_CFG['n_poison'], WW_CFG['n_sensors'])
+    bpe = bytes_per_env_step(a.workload)
     peak, peak_kind = measured_peak_gbs()
     achieved = bpe * E * T / (kern_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": max(3, a.warmup), "ms_per_step": ms / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "MAWaterWorld 5p/5e/10po/30 sensors, %d envs per GPU, %d lockstep "
-                               "env steps per rollout launch, auto-reset (VecEnvExecutor semantics)" % (E, T),
-                   "envs_per_gpu": E, "t_inner": T, "actions": "0.5*N(0,1), HBM-resident",
+        "scaling": "weak", "vs_baseline": None, "dtype": ("u8/int32 + f32 obs" if WL["family"] == "pe" else "f32"),
+        "data": "synthetic",
+        "config": {"workload": WL["desc"] + ", %d envs per GPU, %d lockstep env steps per rollout launch, "
+                               "auto-reset (VecEnvExecutor semantics)" % (E, T),
+                   "envs_per_gpu": E, "t_inner": T,
+                   "actions": ("uniform {0..4}" if WL["family"] == "pe" else "0.5*N(0,1)") + ", HBM-resident",
                    "l2": "outputs per launch (%.0f MB) exceed L2" % (out[0].numel() * 4 / 1e6),
                    "parallelism": "env-shard x%d" % world,
                    "gather": "none" if world == 1 else ("one packed all_gather of rew/done/info per rollout" +
@@ -289,10 +366,11 @@ def main():
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch: 1.0890 GB measured for
                      # one E=4096, T=64 launch (ncu --set full, profiles/r1_ww_kernel_final_full.md),
                      # i.e. 17.0 MB per lockstep step, scaled to this launch's T
-                     "traffic": (1.0890e9 / 64 * T if E == 4096 else None),
+                     "traffic": (1.0890e9 / 64 * T if (E == 4096 and a.workload == "waterworld") else None),
                      "traffic_unit": "bytes per launch (algorithmic: %d)" % (bpe * E * T),
                      "peak_kind": peak_kind,
-                     "kernel": "ww_kernel<float>", "kernel_ms": kern_ms,
+                     "kernel": {"ww": "ww_kernel<float>", "pe": "pe_kernel", "hw": "hw_kernel<float>"}[WL["family"]],
+                     "kernel_ms": kern_ms,
                      "algorithmic_bytes_per_env_step": bpe},
         "gpu_launches": int(launches),
         "clocks": dict(sampler.summary(), window="same rollout workload kept running for 0.8 s right "
@@ -303,12 +381,12 @@ def main():
         line["e2e"] = e2e
     if world == 1 and not a.no_cpu:
         procs = host_cores
-        v = cpu_baseline(a.cpu_seconds, procs)
-        v1 = cpu_baseline(min(4.0, a.cpu_seconds), 1)
+        v = cpu_baseline(a.cpu_seconds, procs, a.workload)
+        v1 = cpu_baseline(min(4.0, a.cpu_seconds), 1, a.workload)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
                                 "single_core_value": v1,
                                 "sample": "%d processes x %.0f s of step() (one env each), float64 NumPy "
-                                          "oracle port of waterworld.py:220-436" % (procs, a.cpu_seconds)}
+                                          "oracle port of the reference step()" % (procs, a.cpu_seconds)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
