@@ -188,6 +188,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--gather-obs", action="store_true",
                     help="also all-gather the full obs tensor every rollout (NVLink-bound)")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="multi-GPU trajectory exchange: fused P2P stores in the kernel, or one NCCL all_gather")
     ap.add_argument("--wpb", type=int, default=0)
     ap.add_argument("--bps", type=int, default=0)
     a = ap.parse_args()
@@ -256,15 +258,33 @@ def main():
     if world > 1 and a.gather_obs:
         g_obs = torch.empty((world * T, E, Np, D), device=dev)
 
+    # Multi-GPU exchange of the per-rollout trajectory tensors (rewards / dones / infos; obs stays
+    # sharded with the data-parallel learner unless --gather-obs).  Default for Waterworld: FUSED --
+    # the rollout kernel stores those rows into every rank's gather buffers over NVLink peer memory
+    # (madrl_b200.dist.PeerGather) and only a tiny completion all-reduce remains; --exchange nccl
+    # uses one packed NCCL all_gather after the kernel instead.
+    peer = None
+    if world > 1 and a.exchange == "fused" and WL["family"] == "ww":
+        from madrl_b200.dist import PeerGather
+        peer = PeerGather(eng, T, Np)
+    step_counter = [0]
+
+    def pre_rollout():
+        if peer is not None:
+            peer.arm(step_counter[0])
+            step_counter[0] += 1
+
     def exchange():
-        # the ONE per-rollout gather of trajectory tensors over NVLink (rewards / dones / infos;
-        # obs stays sharded with the data-parallel learner unless --gather-obs)
         if world > 1:
-            packed.gather_raw()
+            if peer is not None:
+                peer.complete()
+            else:
+                packed.gather_raw()
             if a.gather_obs:
                 dist.all_gather_into_tensor(g_obs, out[0])
 
     def one_step(i):
+        pre_rollout()
         eng.rollout(actions[i % n_act], auto_reset=True, out=out)
         exchange()
 
@@ -285,6 +305,7 @@ def main():
     barrier()
     ev0.record()
     for i in range(a.steps):
+        pre_rollout()
         kev[i][0].record()
         eng.rollout(actions[i % n_act], auto_reset=True, out=out)
         kev[i][1].record()
@@ -304,6 +325,8 @@ def main():
             eng.rollout(actions[i % n_act], auto_reset=True, out=out)
             i += 1
         torch.cuda.synchronize()
+    if peer is not None:
+        peer.close()
     kern_ms = float(np.mean([s.elapsed_time(e) for s, e in kev]))
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -359,8 +382,11 @@ def main():
                    "actions": ("uniform {0..4}" if WL["family"] == "pe" else "0.5*N(0,1)") + ", HBM-resident",
                    "l2": "outputs per launch (%.0f MB) exceed L2" % (out[0].numel() * 4 / 1e6),
                    "parallelism": "env-shard x%d" % world,
-                   "gather": "none" if world == 1 else ("one packed all_gather of rew/done/info per rollout" +
-                                                        (" + obs all_gather" if a.gather_obs else ""))},
+                   "gather": "none" if world == 1 else (
+                       ("rew/done/info stored into every rank's buffers by the rollout kernel over NVLink "
+                        "peer memory + 1 completion all-reduce per rollout" if peer is not None else
+                        "one packed NCCL all_gather of rew/done/info per rollout") +
+                       (" + obs all_gather" if a.gather_obs else ""))},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch: 1.0890 GB measured for

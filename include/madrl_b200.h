@@ -93,6 +93,14 @@ void* madrl_ww_state_ptr(madrl_ww* h);
 int madrl_ww_seed(madrl_ww* h, uint64_t seed, void* stream);
 /* Launch geometry override (0 = library default): warps (= envs) per block <= 4, blocks per SM. */
 int madrl_ww_set_launch(madrl_ww* h, int warps_per_block, int blocks_per_sm);
+/* Fused per-rollout exchange for env-sharded multi-GPU runs: after this call every rollout also
+ * stores its reward / done / info rows into slot `rank` of each listed gather buffer (peer-mapped
+ * device pointers, e.g. CUDA-IPC mappings of the other ranks' buffers over NVLink):
+ *   rew_peers[d]:  real  [n_peers][t_max][E][Np]    done_peers[d]: uint8 [n_peers][t_max][E]
+ *   info_peers[d]: int32 [n_peers][t_max][E][2]
+ * A barrier between the ranks after the rollout completes the gather.  n_peers = 0 disables. */
+int madrl_ww_set_peers(madrl_ww* h, int n_peers, int rank, int t_max, void* const* rew_peers,
+                       void* const* done_peers, void* const* info_peers);
 
 /* reset(): envs with mask_dev[e] != 0 (all if NULL) are re-initialised and advanced by the
  * reference's internal step(zeros); obs_dev real [E][Np][obs_dim], rows of unmasked envs untouched. */

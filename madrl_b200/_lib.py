@@ -97,6 +97,7 @@ def _declare(lib):
     lib.madrl_ww_state_ptr.restype = vp
     lib.madrl_ww_seed.argtypes = [vp, u64, vp]
     lib.madrl_ww_set_launch.argtypes = [vp, i32, i32]
+    lib.madrl_ww_set_peers.argtypes = [vp, i32, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.madrl_ww_reset.argtypes = [vp, vp, vp, vp]
     lib.madrl_ww_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp]
     lib.madrl_ww_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]

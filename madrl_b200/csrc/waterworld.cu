@@ -53,6 +53,14 @@ struct WWParams {
   uint8_t* done;
   int32_t* info;
   const uint8_t* mask;
+  // fused per-rollout exchange (multi-GPU): every rank also stores its reward / done / info rows
+  // straight into slot `peer_rank` of EVERY rank's gather buffers through NVLink peer mappings
+  // (CUDA IPC), so the "gather" costs no separate pass: 29 B per env-step per peer, fire-and-forget.
+  int n_peers, peer_rank;
+  size_t peer_rew_stride, peer_te_stride;   // elements per rank slot: Tmax*E*Np and Tmax*E
+  real* peer_rew[8];
+  uint8_t* peer_done[8];
+  int32_t* peer_info[8];
 };
 
 template <typename real> struct Vec2;
@@ -365,6 +373,10 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
             if ((whoEnc >> lane) & 1u) r += p.encounter_reward;
           }
           store_stream(rew_t, r);
+          if (p.n_peers > 0) {
+            const size_t off = (size_t)p.peer_rank * p.peer_rew_stride + (size_t)(rew_t - p.rew);
+            for (int d = 0; d < p.n_peers; ++d) store_stream(p.peer_rew[d] + off, r);
+          }
         }
         // ---- evaders / poison drift; bounce only if BOTH coordinates left [0,1]: ww:397-409 ---------
 #pragma unroll
@@ -384,6 +396,13 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
           if (lane == 0) {
             p.done[te] = done ? 1 : 0;
             reinterpret_cast<int2*>(p.info)[te] = make_int2(nE, nP);
+            if (p.n_peers > 0) {
+              const size_t off = (size_t)p.peer_rank * p.peer_te_stride + te;
+              for (int d = 0; d < p.n_peers; ++d) {
+                p.peer_done[d][off] = done ? 1 : 0;
+                reinterpret_cast<int2*>(p.peer_info[d])[off] = make_int2(nE, nP);
+              }
+            }
           }
           // VecEnvExecutor.step: a done env is reset in place and its obs slot receives the
           // reset observation (rllab/sandbox/rocky/tf/envs/vec_env_executor.py:24-27)
@@ -426,6 +445,11 @@ struct madrl_ww {
   // staging for the host-buffer entry points (lazily sized)
   void* stage;
   size_t stage_bytes;
+  // peer gather buffers (multi-GPU fused exchange); n_peers == 0: disabled
+  int n_peers, peer_rank, peer_tmax;
+  void* peer_rew[8];
+  void* peer_done[8];
+  void* peer_info[8];
 };
 
 static int ww_validate(const madrl_ww_config* c) {
@@ -495,6 +519,7 @@ extern "C" int madrl_ww_create(const madrl_ww_config* c, void* state_dev, madrl_
   h->stage_bytes = 0;
   h->warps_per_block = 0;
   h->blocks_per_sm = 0;
+  h->n_peers = 0; h->peer_rank = 0; h->peer_tmax = 0;
   cudaError_t e = cudaGetDevice(&h->device);
   if (e != cudaSuccess) { set_error("cudaGetDevice: %s", cudaGetErrorString(e)); delete h; return MADRL_ECUDA; }
   h->sms = sm_count(h->device);
@@ -530,6 +555,21 @@ extern "C" int madrl_ww_seed(madrl_ww* h, uint64_t seed, void* stream) {
   h->cfg.seed = seed;
   MADRL_CUDA_CHECK(cudaMemsetAsync(h->state + h->lay.rng_counter, 0, 8 * (size_t)h->cfg.n_envs,
                                    (cudaStream_t)stream));
+  return MADRL_OK;
+}
+
+extern "C" int madrl_ww_set_peers(madrl_ww* h, int n_peers, int rank, int t_max, void* const* rew_peers,
+                                  void* const* done_peers, void* const* info_peers) {
+  MADRL_REQUIRE(h != nullptr, "handle is NULL");
+  MADRL_REQUIRE(n_peers >= 0 && n_peers <= 8, "n_peers must be in [0,8], got %d", n_peers);
+  if (n_peers == 0) { h->n_peers = 0; return MADRL_OK; }
+  MADRL_REQUIRE(rank >= 0 && rank < n_peers && t_max >= 1, "bad rank / t_max");
+  MADRL_REQUIRE(rew_peers && done_peers && info_peers, "NULL peer pointer table");
+  for (int d = 0; d < n_peers; ++d) {
+    MADRL_REQUIRE(rew_peers[d] && done_peers[d] && info_peers[d], "NULL peer buffer %d", d);
+    h->peer_rew[d] = rew_peers[d]; h->peer_done[d] = done_peers[d]; h->peer_info[d] = info_peers[d];
+  }
+  h->n_peers = n_peers; h->peer_rank = rank; h->peer_tmax = t_max;
   return MADRL_OK;
 }
 
@@ -610,6 +650,18 @@ static int ww_launch(madrl_ww* h, int mode, int T, const void* actions, void* ob
   p.sensors = (const real*)(st + h->lay.sensors);
   p.actions = (const real*)actions; p.obs = (real*)obs; p.rew = (real*)rew;
   p.done = done; p.info = info; p.mask = mask;
+  p.n_peers = (mode == 0) ? h->n_peers : 0;
+  p.peer_rank = h->peer_rank;
+  if (p.n_peers > 0) {
+    MADRL_REQUIRE(T <= h->peer_tmax, "rollout of %d steps exceeds the peer buffers (t_max %d)", T, h->peer_tmax);
+    p.peer_rew_stride = (size_t)h->peer_tmax * p.E * p.Np;
+    p.peer_te_stride = (size_t)h->peer_tmax * p.E;
+    for (int d = 0; d < 8; ++d) {
+      p.peer_rew[d] = (real*)h->peer_rew[d % p.n_peers];
+      p.peer_done[d] = (uint8_t*)h->peer_done[d % p.n_peers];
+      p.peer_info[d] = (int32_t*)h->peer_info[d % p.n_peers];
+    }
+  }
 
   const int opl = (p.Nall + 31) / 32, kch = (p.K + 31) / 32;
 #define MADRL_WW_CASE(O, KH, KC_) return ww_launch_inst<real, O, KH, KC_>(h, p, stream)

@@ -123,3 +123,58 @@ class PackedTrajectory(object):
                 self._gbuf = torch.empty(world * self.nbytes, dtype=torch.uint8, device=self.buf.device)
             dist.all_gather_into_tensor(self._gbuf, self.buf, group=group)
         return self._gbuf
+
+
+class PeerGather(object):
+    """Fused per-rollout exchange over NVLink peer memory (no separate collective pass).
+
+    Every rank allocates gather buffers ``rew [W, Tmax, E, A]``, ``done [W, Tmax, E]``,
+    ``info [W, Tmax, E, 2]`` (double-buffered), shares them with the other ranks through CUDA IPC
+    (torch's own tensor-sharing reduction, exchanged with ``all_gather_object``) and hands the peer
+    mappings to the engine (``madrl_ww_set_peers``): the rollout kernel then stores each env's
+    reward / done / info rows into slot ``rank`` of EVERY rank's buffers while it computes.  What is
+    left of the "gather" is ``complete()``: one tiny all-reduce that orders every rank's kernel
+    completion before the buffers are read.  Buffers alternate between two sets so that a fast rank
+    writing rollout k+1 never touches the set a slow rank is still reading for rollout k.
+    """
+
+    def __init__(self, engine, t_max, n_agents, info_width=2, n_sets=2, group=None):
+        from torch.multiprocessing.reductions import reduce_tensor
+        assert dist.is_initialized()
+        self.engine, self.group, self.t_max = engine, group, t_max
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        dev, E, W = engine.device, engine.n_envs, self.world
+        self.sets, self._peers = [], []
+        for _ in range(n_sets):
+            local = (torch.zeros((W, t_max, E, n_agents), dtype=engine.dtype, device=dev),
+                     torch.zeros((W, t_max, E), dtype=torch.uint8, device=dev),
+                     torch.zeros((W, t_max, E, info_width), dtype=torch.int32, device=dev))
+            torch.cuda.synchronize(dev)
+            mine = [reduce_tensor(t) for t in local]            # (rebuild_fn, args) -- picklable IPC handles
+            everyone = [None] * W
+            dist.all_gather_object(everyone, mine, group=group)
+            peers = ([], [], [])
+            for r in range(W):
+                for k in range(3):
+                    peers[k].append(local[k] if r == self.rank else everyone[r][k][0](*everyone[r][k][1]))
+            self.sets.append(local)
+            self._peers.append(peers)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._cur = -1
+
+    def arm(self, k):
+        """Direct the next rollout's exchange at buffer set k % n_sets; returns that set."""
+        self._cur = k % len(self.sets)
+        pr, pd, pi = self._peers[self._cur]
+        self.engine.set_peers(self.rank, self.t_max, pr, pd, pi)
+        return self.sets[self._cur]
+
+    def complete(self):
+        """Order all ranks' rollout kernels before the gathered buffers are read (stream-ordered)."""
+        dist.all_reduce(self._flag, group=self.group)
+        return self.sets[self._cur]
+
+    def close(self):
+        self.engine.clear_peers()
+        dist.barrier(group=self.group)
+        self._peers = []

@@ -122,6 +122,19 @@ class BatchedMAWaterWorld(object):
     def set_launch(self, warps_per_block=0, blocks_per_sm=0):
         _lib.check(self._L.madrl_ww_set_launch(self._h, warps_per_block, blocks_per_sm))
 
+    def set_peers(self, rank, t_max, rew_peers, done_peers, info_peers):
+        """Enable the fused exchange: `*_peers` are lists (one per rank, this rank included) of
+        tensors aliasing every rank's gather buffers (see madrl_b200.dist.PeerGather)."""
+        n = len(rew_peers)
+        arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+        self._peer_keepalive = (rew_peers, done_peers, info_peers)
+        _lib.check(self._L.madrl_ww_set_peers(self._h, n, rank, t_max, arr(rew_peers), arr(done_peers),
+                                              arr(info_peers)))
+
+    def clear_peers(self):
+        self._peer_keepalive = None
+        _lib.check(self._L.madrl_ww_set_peers(self._h, 0, 0, 0, None, None, None))
+
     # ------------------------------------------------------------------ env surface (batched)
     def seed(self, seed=None):
         self._seed = 0 if seed is None else int(seed)

@@ -1,0 +1,64 @@
+"""Fused NVLink peer-memory exchange (needs >= 2 GPUs; skipped on the single-GPU test box):
+the gather buffers every rank ends up with must equal the stacked per-rank rollouts."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from madrl_b200 import BatchedMAWaterWorld
+    from madrl_b200.dist import PeerGather
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        E, T, Np = 96, 12, 5
+        eng = BatchedMAWaterWorld(E, Np, 5, device=dev, seed=9, env_id_base=rank * E, n_coop=1, radius=0.04)
+        eng.reset()
+        pg = PeerGather(eng, T, Np)
+        ok = True
+        for k in range(3):                                  # exercises both buffer sets
+            act = torch.randn(T, E, Np, 2, device=dev, generator=torch.Generator(dev).manual_seed(100 * k + rank)) * 0.7
+            pg.arm(k)
+            obs, rew, done, info = eng.rollout(act, auto_reset=True)
+            g_rew, g_done, g_info = pg.complete()
+            torch.cuda.synchronize()
+            # reference exchange: plain NCCL all_gather of the local outputs
+            r_rew = torch.empty((world,) + tuple(rew.shape), device=dev)
+            dist.all_gather_into_tensor(r_rew.view(world * T, E, Np), rew)
+            r_info = torch.empty((world,) + tuple(info.shape), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(r_info.view(world * T, E, 2), info)
+            r_done = torch.empty((world,) + tuple(done.shape), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(r_done.view(world * T, E), done)
+            ok = ok and torch.equal(g_rew, r_rew) and torch.equal(g_info, r_info) and torch.equal(g_done, r_done)
+        pg.close()
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_exchange_equals_nccl_all_gather():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    world = 2
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    res = dict(q.get() for _ in range(world))
+    assert res == {0: True, 1: True}
