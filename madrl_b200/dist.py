@@ -157,8 +157,21 @@ class PeerGather(object):
             for r in range(W):
                 for k in range(3):
                     peers[k].append(local[k] if r == self.rank else everyone[r][k][0](*everyone[r][k][1]))
+            # The IPC mappings live on the exporting device; a kernel on THIS device may only
+            # dereference them once peer access dev -> peer is enabled.  torch enables it (both
+            # directions) the first time it copies between the two devices, so touch every mapping.
+            for k in range(3):
+                for r in range(W):
+                    if r != self.rank:
+                        assert torch.cuda.can_device_access_peer(dev.index, peers[k][r].device.index), \
+                            "no NVLink/PCIe peer access between cuda:%d and cuda:%d" % (dev.index, peers[k][r].device.index)
+                        probe = torch.empty(1, dtype=peers[k][r].dtype, device=dev)
+                        probe.copy_(peers[k][r].reshape(-1)[:1])
+                        peers[k][r].reshape(-1)[:1].copy_(probe)
+            torch.cuda.synchronize(dev)
             self.sets.append(local)
             self._peers.append(peers)
+        dist.barrier(group=group)
         self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._cur = -1
 
