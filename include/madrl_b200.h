@@ -53,6 +53,14 @@ int madrl_version(void);
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 uint64_t madrl_launch_count(void);
 
+/* CUDA-IPC buffers for the fused multi-GPU exchange (see madrl_ww_set_peers): allocate + export on
+ * the owning rank, open on every other rank with ITS device current (peer access over NVLink is
+ * enabled lazily), close / free at teardown.  handle64 is the 64-byte cudaIpcMemHandle_t. */
+int madrl_ipc_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int madrl_ipc_open(const unsigned char* handle64, void** ptr);
+int madrl_ipc_close(void* ptr);
+int madrl_ipc_free(void* ptr);
+
 /* ------------------------------------------------------------------ MAWaterWorld ------------ */
 typedef struct madrl_ww_config {
   int32_t n_envs;          /* envs in THIS handle (the local shard)                              */

@@ -90,6 +90,10 @@ def _declare(lib):
     lib.madrl_last_error.restype = C.c_char_p
     lib.madrl_version.restype = C.c_int
     lib.madrl_launch_count.restype = C.c_uint64
+    lib.madrl_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
+    lib.madrl_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.madrl_ipc_close.argtypes = [vp]
+    lib.madrl_ipc_free.argtypes = [vp]
     lib.madrl_ww_state_layout.argtypes = [C.POINTER(WWConfig), C.POINTER(WWLayout)]
     lib.madrl_ww_create.argtypes = [C.POINTER(WWConfig), vp, C.POINTER(vp)]
     lib.madrl_ww_destroy.argtypes = [vp]

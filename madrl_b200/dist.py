@@ -125,52 +125,70 @@ class PackedTrajectory(object):
         return self._gbuf
 
 
+class _DevBuf(object):
+    """A raw device allocation exposed to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr, nbytes):
+        self.ptr, self.nbytes = ptr, nbytes
+        self.__cuda_array_interface__ = dict(shape=(nbytes,), typestr="|u1", data=(ptr, False), version=2)
+
+
 class PeerGather(object):
     """Fused per-rollout exchange over NVLink peer memory (no separate collective pass).
 
-    Every rank allocates gather buffers ``rew [W, Tmax, E, A]``, ``done [W, Tmax, E]``,
-    ``info [W, Tmax, E, 2]`` (double-buffered), shares them with the other ranks through CUDA IPC
-    (torch's own tensor-sharing reduction, exchanged with ``all_gather_object``) and hands the peer
-    mappings to the engine (``madrl_ww_set_peers``): the rollout kernel then stores each env's
-    reward / done / info rows into slot ``rank`` of EVERY rank's buffers while it computes.  What is
-    left of the "gather" is ``complete()``: one tiny all-reduce that orders every rank's kernel
-    completion before the buffers are read.  Buffers alternate between two sets so that a fast rank
-    writing rollout k+1 never touches the set a slow rank is still reading for rollout k.
+    Every rank allocates (double-buffered) gather buffers ``rew [W, Tmax, E, A]``,
+    ``done [W, Tmax, E]``, ``info [W, Tmax, E, 2]`` with ``madrl_ipc_alloc``, the 64-byte CUDA IPC
+    handles are exchanged with ``all_gather_object``, every rank opens its peers' buffers with its
+    own device current (``madrl_ipc_open``) and hands the mappings to the engine
+    (``madrl_ww_set_peers``): the rollout kernel then stores each env's reward / done / info rows
+    into slot ``rank`` of EVERY rank's buffers while it computes.  What is left of the "gather" is
+    ``complete()``: one tiny all-reduce that orders every rank's kernel completion before the
+    buffers are read.  The two buffer sets alternate so that a fast rank writing rollout k+1 never
+    touches the set a slow rank is still reading for rollout k.
     """
 
     def __init__(self, engine, t_max, n_agents, info_width=2, n_sets=2, group=None):
-        from torch.multiprocessing.reductions import reduce_tensor
+        import ctypes as C
+        from . import _lib
         assert dist.is_initialized()
+        self._L = _lib.lib()
         self.engine, self.group, self.t_max = engine, group, t_max
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         dev, E, W = engine.device, engine.n_envs, self.world
-        self.sets, self._peers = [], []
-        for _ in range(n_sets):
-            local = (torch.zeros((W, t_max, E, n_agents), dtype=engine.dtype, device=dev),
-                     torch.zeros((W, t_max, E), dtype=torch.uint8, device=dev),
-                     torch.zeros((W, t_max, E, info_width), dtype=torch.int32, device=dev))
-            torch.cuda.synchronize(dev)
-            mine = [reduce_tensor(t) for t in local]            # (rebuild_fn, args) -- picklable IPC handles
-            everyone = [None] * W
-            dist.all_gather_object(everyone, mine, group=group)
-            peers = ([], [], [])
-            for r in range(W):
-                for k in range(3):
-                    peers[k].append(local[k] if r == self.rank else everyone[r][k][0](*everyone[r][k][1]))
-            # The IPC mappings live on the exporting device; a kernel on THIS device may only
-            # dereference them once peer access dev -> peer is enabled.  torch enables it (both
-            # directions) the first time it copies between the two devices, so touch every mapping.
-            for k in range(3):
+        esz = torch.empty((), dtype=engine.dtype).element_size()
+        r_b = W * t_max * E * n_agents * esz
+        d_b = (W * t_max * E + 255) // 256 * 256
+        i_b = W * t_max * E * info_width * 4
+        nbytes = r_b + i_b + d_b
+
+        def views(buf_u8):
+            return (buf_u8[:r_b].view(engine.dtype).view(W, t_max, E, n_agents),
+                    buf_u8[r_b + i_b:r_b + i_b + W * t_max * E].view(W, t_max, E),
+                    buf_u8[r_b:r_b + i_b].view(torch.int32).view(W, t_max, E, info_width))
+
+        self.sets, self._peers, self._own, self._opened = [], [], [], []
+        with torch.cuda.device(dev):
+            for _ in range(n_sets):
+                ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+                _lib.check(self._L.madrl_ipc_alloc(nbytes, C.byref(ptr), handle))
+                self._own.append(ptr.value)
+                everyone = [None] * W
+                dist.all_gather_object(everyone, handle.raw, group=group)
+                peers = ([], [], [])
                 for r in range(W):
-                    if r != self.rank:
-                        assert torch.cuda.can_device_access_peer(dev.index, peers[k][r].device.index), \
-                            "no NVLink/PCIe peer access between cuda:%d and cuda:%d" % (dev.index, peers[k][r].device.index)
-                        probe = torch.empty(1, dtype=peers[k][r].dtype, device=dev)
-                        probe.copy_(peers[k][r].reshape(-1)[:1])
-                        peers[k][r].reshape(-1)[:1].copy_(probe)
+                    if r == self.rank:
+                        base = ptr.value
+                    else:
+                        q = C.c_void_p()
+                        _lib.check(self._L.madrl_ipc_open(everyone[r], C.byref(q)))
+                        self._opened.append(q.value)
+                        base = q.value
+                    v = views(torch.as_tensor(_DevBuf(base, nbytes), device=dev))
+                    for k in range(3):
+                        peers[k].append(v[k])
+                self.sets.append(tuple(peers[k][self.rank] for k in range(3)))
+                self._peers.append(peers)
             torch.cuda.synchronize(dev)
-            self.sets.append(local)
-            self._peers.append(peers)
         dist.barrier(group=group)
         self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._cur = -1
@@ -183,11 +201,19 @@ class PeerGather(object):
         return self.sets[self._cur]
 
     def complete(self):
-        """Order all ranks' rollout kernels before the gathered buffers are read (stream-ordered)."""
+        """Order all ranks' rollout kernels before the gathered buffers are read (stream-ordered).
+        Returns (rew [W,Tmax,E,A], done [W,Tmax,E], info [W,Tmax,E,2]) of the armed set."""
         dist.all_reduce(self._flag, group=self.group)
         return self.sets[self._cur]
 
     def close(self):
         self.engine.clear_peers()
+        torch.cuda.synchronize(self.engine.device)
         dist.barrier(group=self.group)
-        self._peers = []
+        with torch.cuda.device(self.engine.device):
+            for q in self._opened:
+                self._L.madrl_ipc_close(q)
+            dist.barrier(group=self.group)
+            for q in self._own:
+                self._L.madrl_ipc_free(q)
+        self._opened, self._own, self._peers, self.sets = [], [], [], []
