@@ -188,8 +188,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--gather-obs", action="store_true",
                     help="also all-gather the full obs tensor every rollout (NVLink-bound)")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
-                    help="multi-GPU trajectory exchange: fused P2P stores in the kernel, or one NCCL all_gather")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "fused-all", "nccl"],
+                    help="multi-GPU trajectory exchange: fused NVLink peer stores in the rollout kernel "
+                         "(gather to rank 0, or to every rank), or one packed NCCL all_gather")
     ap.add_argument("--wpb", type=int, default=0)
     ap.add_argument("--bps", type=int, default=0)
     a = ap.parse_args()
@@ -263,10 +264,18 @@ def main():
     # the rollout kernel stores those rows into every rank's gather buffers over NVLink peer memory
     # (madrl_b200.dist.PeerGather) and only a tiny completion all-reduce remains; --exchange nccl
     # uses one packed NCCL all_gather after the kernel instead.
-    peer = None
-    if world > 1 and a.exchange == "fused" and WL["family"] == "ww":
+    peer, peer_note = None, None
+    if world > 1 and a.exchange != "nccl" and WL["family"] == "ww":
         from madrl_b200.dist import PeerGather
-        peer = PeerGather(eng, T, Np)
+        try:   # every rank must take the same branch: agree on success with an all-reduce
+            peer = PeerGather(eng, T, Np, mode="all" if a.exchange == "fused-all" else "root")
+            okf = torch.ones(1, device=dev)
+        except Exception as ex:   # e.g. no peer access between the GPUs of this box
+            peer, peer_note, okf = None, "fused exchange unavailable (%s)" % type(ex).__name__, torch.zeros(1, device=dev)
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        if okf.item() == 0 and peer is not None:
+            peer.close()
+            peer, peer_note = None, "fused exchange unavailable on another rank"
     step_counter = [0]
 
     def pre_rollout():
@@ -383,9 +392,11 @@ def main():
                    "l2": "outputs per launch (%.0f MB) exceed L2" % (out[0].numel() * 4 / 1e6),
                    "parallelism": "env-shard x%d" % world,
                    "gather": "none" if world == 1 else (
-                       ("rew/done/info stored into every rank's buffers by the rollout kernel over NVLink "
-                        "peer memory + 1 completion all-reduce per rollout" if peer is not None else
-                        "one packed NCCL all_gather of rew/done/info per rollout") +
+                       ("rew/done/info rows stored by the rollout kernel into %s gather buffers over NVLink "
+                        "peer memory + 1 completion all-reduce per rollout"
+                        % ("every rank's" if a.exchange == "fused-all" else "rank 0's") if peer is not None else
+                        "one packed NCCL all_gather of rew/done/info per rollout" +
+                        (" [%s]" % peer_note if peer_note else "")) +
                        (" + obs all_gather" if a.gather_obs else ""))},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,

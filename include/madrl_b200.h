@@ -102,13 +102,15 @@ int madrl_ww_seed(madrl_ww* h, uint64_t seed, void* stream);
 /* Launch geometry override (0 = library default): warps (= envs) per block <= 4, blocks per SM. */
 int madrl_ww_set_launch(madrl_ww* h, int warps_per_block, int blocks_per_sm);
 /* Fused per-rollout exchange for env-sharded multi-GPU runs: after this call every rollout also
- * stores its reward / done / info rows into slot `rank` of each listed gather buffer (peer-mapped
- * device pointers, e.g. CUDA-IPC mappings of the other ranks' buffers over NVLink):
- *   rew_peers[d]:  real  [n_peers][t_max][E][Np]    done_peers[d]: uint8 [n_peers][t_max][E]
- *   info_peers[d]: int32 [n_peers][t_max][E][2]
- * A barrier between the ranks after the rollout completes the gather.  n_peers = 0 disables. */
-int madrl_ww_set_peers(madrl_ww* h, int n_peers, int rank, int t_max, void* const* rew_peers,
-                       void* const* done_peers, void* const* info_peers);
+ * stores its reward / done / info rows into slot `slot` of each of the `n_dest` listed gather
+ * buffers (peer-mapped device pointers: CUDA-IPC mappings of other ranks' buffers over NVLink; one
+ * destination = gather-to-root, world destinations = all-gather).  Env-major layout per buffer:
+ *   rew  real  [n_slots][E][t_max][Np]    done uint8 [n_slots][E][t_max]
+ *   info int32 [n_slots][E][t_max][2]
+ * Rows are staged in registers and written as coalesced runs.  A stream-ordered barrier between the
+ * ranks after the rollout completes the gather.  n_dest = 0 disables. */
+int madrl_ww_set_peers(madrl_ww* h, int n_dest, int slot, int t_max, void* const* rew_dest,
+                       void* const* done_dest, void* const* info_dest);
 
 /* reset(): envs with mask_dev[e] != 0 (all if NULL) are re-initialised and advanced by the
  * reference's internal step(zeros); obs_dev real [E][Np][obs_dim], rows of unmasked envs untouched. */

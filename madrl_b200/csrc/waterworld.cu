@@ -54,10 +54,11 @@ struct WWParams {
   int32_t* info;
   const uint8_t* mask;
   // fused per-rollout exchange (multi-GPU): every rank also stores its reward / done / info rows
-  // straight into slot `peer_rank` of EVERY rank's gather buffers through NVLink peer mappings
-  // (CUDA IPC), so the "gather" costs no separate pass: 29 B per env-step per peer, fire-and-forget.
-  int n_peers, peer_rank;
-  size_t peer_rew_stride, peer_te_stride;   // elements per rank slot: Tmax*E*Np and Tmax*E
+  // into slot `peer_rank` of each destination gather buffer through NVLink peer mappings (CUDA
+  // IPC).  Rows are staged in registers and written as coalesced runs (rewards every 32/Np steps,
+  // done/info every 32 steps) into an ENV-major layout [slot][E][Tmax][...], because thousands of
+  // 4-byte remote stores per step cost far more than the bytes they carry.
+  int n_peers, peer_rank, peer_tmax;
   real* peer_rew[8];
   uint8_t* peer_done[8];
   int32_t* peer_info[8];
@@ -110,7 +111,9 @@ __device__ __noinline__ Spawn<real> spawn_object(uint64_t seed, uint32_t env_id,
 #ifndef MADRL_WW_MINBLOCKS_OPL4
 #define MADRL_WW_MINBLOCKS_OPL4 7   // resident 128-thread blocks per SM requested for 65..128 objects
 #endif
-template <typename real, int OPL, int KCH, int KC>
+// PEER = compile the fused multi-GPU exchange in (a separate instantiation, so the single-GPU kernel
+// carries none of its registers).
+template <typename real, int OPL, int KCH, int KC, bool PEER>
 __global__ void __launch_bounds__(128, (OPL <= 2 ? 7 : (OPL <= 4 ? MADRL_WW_MINBLOCKS_OPL4 : 4)))
 ww_kernel(const __grid_constant__ WWParams<real> p) {
   const real INF = real_inf<real>();
@@ -173,6 +176,15 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     size_t te = (size_t)e;   // index of (t, e) in the [T][E] done / info tensors
     int pass = (p.mode == 1) ? 1 : 0;  // pass 1 = reset pass: fresh draws, zero action, obs only
     const V2* act_t = reinterpret_cast<const V2*>(p.actions) + (size_t)e * p.Np + lane;
+
+    // staging registers of the fused exchange
+    const int rew_per = 32 / p.Np;                       // steps per coalesced reward run
+    const int stage_src = lane % p.Np, stage_step = lane / p.Np;
+    const size_t peer_env = (size_t)p.peer_rank * p.E + e;
+    real st_rew = 0, r_stage = 0;
+    int2 st_info = make_int2(0, 0);
+    uint8_t st_done = 0;
+    int sc_rew = 0;
 
     for (int t = 0; t < p.T; ++t) {
       V2 act;
@@ -373,9 +385,17 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
             if ((whoEnc >> lane) & 1u) r += p.encounter_reward;
           }
           store_stream(rew_t, r);
-          if (p.n_peers > 0) {
-            const size_t off = (size_t)p.peer_rank * p.peer_rew_stride + (size_t)(rew_t - p.rew);
-            for (int d = 0; d < p.n_peers; ++d) store_stream(p.peer_rew[d] + off, r);
+          if (PEER) r_stage = r;
+        }
+        if (PEER && !pass && p.n_peers > 0) {   // stage this step's rewards: lane s*Np + a <- (step s, agent a)
+          const real v = __shfl_sync(FULL_MASK, r_stage, stage_src);
+          if (stage_step == sc_rew) st_rew = v;
+          if (++sc_rew == rew_per) {
+            if (lane < rew_per * p.Np) {
+              const size_t off = (peer_env * p.peer_tmax + (size_t)(t + 1 - rew_per)) * p.Np + lane;
+              for (int d = 0; d < p.n_peers; ++d) store_stream(p.peer_rew[d] + off, st_rew);
+            }
+            sc_rew = 0;
           }
         }
         // ---- evaders / poison drift; bounce only if BOTH coordinates left [0,1]: ww:397-409 ---------
@@ -396,11 +416,16 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
           if (lane == 0) {
             p.done[te] = done ? 1 : 0;
             reinterpret_cast<int2*>(p.info)[te] = make_int2(nE, nP);
-            if (p.n_peers > 0) {
-              const size_t off = (size_t)p.peer_rank * p.peer_te_stride + te;
-              for (int d = 0; d < p.n_peers; ++d) {
-                p.peer_done[d][off] = done ? 1 : 0;
-                reinterpret_cast<int2*>(p.peer_info[d])[off] = make_int2(nE, nP);
+          }
+          if (PEER && p.n_peers > 0) {  // stage done / info of step t in lane t % 32; flush every 32 steps
+            if (lane == (t & 31)) { st_info = make_int2(nE, nP); st_done = done ? 1 : 0; }
+            if ((t & 31) == 31 || t == p.T - 1) {
+              if (lane <= (t & 31)) {
+                const size_t off = peer_env * p.peer_tmax + (size_t)(t & ~31) + lane;
+                for (int d = 0; d < p.n_peers; ++d) {
+                  p.peer_done[d][off] = st_done;
+                  reinterpret_cast<int2*>(p.peer_info[d])[off] = st_info;
+                }
               }
             }
           }
@@ -414,6 +439,10 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
       act_t += (size_t)p.E * p.Np;
       rew_t += (size_t)p.E * p.Np;
       te += (size_t)p.E;
+    }
+    if (PEER && p.n_peers > 0 && sc_rew > 0 && lane < sc_rew * p.Np) {   // partial reward run at the end
+      const size_t off = (peer_env * p.peer_tmax + (size_t)(p.T - sc_rew)) * p.Np + lane;
+      for (int d = 0; d < p.n_peers; ++d) store_stream(p.peer_rew[d] + off, st_rew);
     }
     // ---- registers -> HBM record ------------------------------------------------------------------
 #pragma unroll
@@ -563,7 +592,7 @@ extern "C" int madrl_ww_set_peers(madrl_ww* h, int n_peers, int rank, int t_max,
   MADRL_REQUIRE(h != nullptr, "handle is NULL");
   MADRL_REQUIRE(n_peers >= 0 && n_peers <= 8, "n_peers must be in [0,8], got %d", n_peers);
   if (n_peers == 0) { h->n_peers = 0; return MADRL_OK; }
-  MADRL_REQUIRE(rank >= 0 && rank < n_peers && t_max >= 1, "bad rank / t_max");
+  MADRL_REQUIRE(rank >= 0 && t_max >= 1, "bad slot / t_max");
   MADRL_REQUIRE(rew_peers && done_peers && info_peers, "NULL peer pointer table");
   for (int d = 0; d < n_peers; ++d) {
     MADRL_REQUIRE(rew_peers[d] && done_peers[d] && info_peers[d], "NULL peer buffer %d", d);
@@ -594,19 +623,25 @@ static real exact_sq_threshold(double thr_d) {
   return t;
 }
 
-template <typename real, int OPL, int KCH, int KC>
-static int ww_launch_inst(madrl_ww* h, const WWParams<real>& p, cudaStream_t stream) {
+template <typename real, int OPL, int KCH, int KC, bool PEER>
+static int ww_launch_inst2(madrl_ww* h, const WWParams<real>& p, cudaStream_t stream) {
   const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 4;
   int resident = 0;
-  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ww_kernel<real, OPL, KCH, KC>, wpb * 32, 0));
+  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ww_kernel<real, OPL, KCH, KC, PEER>, wpb * 32, 0));
   if (resident < 1) resident = 1;
   if (h->blocks_per_sm > 0 && h->blocks_per_sm < resident) resident = h->blocks_per_sm;
   int grid = (p.E + wpb - 1) / wpb;                  // one warp per env ...
   if (grid > h->sms * resident) grid = h->sms * resident;  // ... or a single persistent wave
-  ww_kernel<real, OPL, KCH, KC><<<grid, wpb * 32, 0, stream>>>(p);
+  ww_kernel<real, OPL, KCH, KC, PEER><<<grid, wpb * 32, 0, stream>>>(p);
   g_launches.fetch_add(1);
   MADRL_CUDA_CHECK(cudaGetLastError());
   return MADRL_OK;
+}
+
+template <typename real, int OPL, int KCH, int KC>
+static int ww_launch_inst(madrl_ww* h, const WWParams<real>& p, cudaStream_t stream) {
+  return p.n_peers > 0 ? ww_launch_inst2<real, OPL, KCH, KC, true>(h, p, stream)
+                       : ww_launch_inst2<real, OPL, KCH, KC, false>(h, p, stream);
 }
 
 template <typename real>
@@ -654,8 +689,7 @@ static int ww_launch(madrl_ww* h, int mode, int T, const void* actions, void* ob
   p.peer_rank = h->peer_rank;
   if (p.n_peers > 0) {
     MADRL_REQUIRE(T <= h->peer_tmax, "rollout of %d steps exceeds the peer buffers (t_max %d)", T, h->peer_tmax);
-    p.peer_rew_stride = (size_t)h->peer_tmax * p.E * p.Np;
-    p.peer_te_stride = (size_t)h->peer_tmax * p.E;
+    p.peer_tmax = h->peer_tmax;
     for (int d = 0; d < 8; ++d) {
       p.peer_rew[d] = (real*)h->peer_rew[d % p.n_peers];
       p.peer_done[d] = (uint8_t*)h->peer_done[d % p.n_peers];

@@ -136,24 +136,31 @@ class _DevBuf(object):
 class PeerGather(object):
     """Fused per-rollout exchange over NVLink peer memory (no separate collective pass).
 
-    Every rank allocates (double-buffered) gather buffers ``rew [W, Tmax, E, A]``,
-    ``done [W, Tmax, E]``, ``info [W, Tmax, E, 2]`` with ``madrl_ipc_alloc``, the 64-byte CUDA IPC
-    handles are exchanged with ``all_gather_object``, every rank opens its peers' buffers with its
-    own device current (``madrl_ipc_open``) and hands the mappings to the engine
-    (``madrl_ww_set_peers``): the rollout kernel then stores each env's reward / done / info rows
-    into slot ``rank`` of EVERY rank's buffers while it computes.  What is left of the "gather" is
-    ``complete()``: one tiny all-reduce that orders every rank's kernel completion before the
-    buffers are read.  The two buffer sets alternate so that a fast rank writing rollout k+1 never
-    touches the set a slow rank is still reading for rollout k.
+    The receiving ranks (``mode='root'``: rank ``root`` only, like the reference's master process
+    that collects the workers' paths; ``mode='all'``: every rank) allocate double-buffered gather
+    buffers with ``madrl_ipc_alloc`` in an env-major layout
+
+        rew [W, E, Tmax, A]     done [W, E, Tmax]     info [W, E, Tmax, 2]
+
+    The 64-byte CUDA IPC handles are exchanged with ``all_gather_object``; every rank opens the
+    destination buffers with its own device current (``madrl_ipc_open``) and hands the mappings to
+    the engine (``madrl_ww_set_peers``).  The rollout kernel then writes each env's reward / done /
+    info rows into slot ``rank`` of every destination buffer while it computes (rows staged in
+    registers, coalesced runs over NVLink).  What is left of the "gather" is ``complete()``: one tiny
+    all-reduce that orders every rank's kernel completion before the buffers are read.  The two
+    buffer sets alternate so that a fast rank writing rollout k+1 never touches the set a slow rank
+    is still reading for rollout k.
     """
 
-    def __init__(self, engine, t_max, n_agents, info_width=2, n_sets=2, group=None):
+    def __init__(self, engine, t_max, n_agents, info_width=2, n_sets=2, group=None, mode="root", root=0):
         import ctypes as C
         from . import _lib
-        assert dist.is_initialized()
+        assert dist.is_initialized() and mode in ("root", "all")
         self._L = _lib.lib()
         self.engine, self.group, self.t_max = engine, group, t_max
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.receivers = [root] if mode == "root" else list(range(self.world))
+        self.is_receiver = self.rank in self.receivers
         dev, E, W = engine.device, engine.n_envs, self.world
         esz = torch.empty((), dtype=engine.dtype).element_size()
         r_b = W * t_max * E * n_agents * esz
@@ -162,20 +169,22 @@ class PeerGather(object):
         nbytes = r_b + i_b + d_b
 
         def views(buf_u8):
-            return (buf_u8[:r_b].view(engine.dtype).view(W, t_max, E, n_agents),
-                    buf_u8[r_b + i_b:r_b + i_b + W * t_max * E].view(W, t_max, E),
-                    buf_u8[r_b:r_b + i_b].view(torch.int32).view(W, t_max, E, info_width))
+            return (buf_u8[:r_b].view(engine.dtype).view(W, E, t_max, n_agents),
+                    buf_u8[r_b + i_b:r_b + i_b + W * t_max * E].view(W, E, t_max),
+                    buf_u8[r_b:r_b + i_b].view(torch.int32).view(W, E, t_max, info_width))
 
-        self.sets, self._peers, self._own, self._opened = [], [], [], []
+        self.sets, self._dest, self._own, self._opened = [], [], [], []
         with torch.cuda.device(dev):
             for _ in range(n_sets):
                 ptr, handle = C.c_void_p(), C.create_string_buffer(64)
-                _lib.check(self._L.madrl_ipc_alloc(nbytes, C.byref(ptr), handle))
-                self._own.append(ptr.value)
+                if self.is_receiver:
+                    _lib.check(self._L.madrl_ipc_alloc(nbytes, C.byref(ptr), handle))
+                    self._own.append(ptr.value)
                 everyone = [None] * W
-                dist.all_gather_object(everyone, handle.raw, group=group)
-                peers = ([], [], [])
-                for r in range(W):
+                dist.all_gather_object(everyone, handle.raw if self.is_receiver else None, group=group)
+                dest = ([], [], [])
+                local = None
+                for r in self.receivers:
                     if r == self.rank:
                         base = ptr.value
                     else:
@@ -184,25 +193,27 @@ class PeerGather(object):
                         self._opened.append(q.value)
                         base = q.value
                     v = views(torch.as_tensor(_DevBuf(base, nbytes), device=dev))
+                    if r == self.rank:
+                        local = v
                     for k in range(3):
-                        peers[k].append(v[k])
-                self.sets.append(tuple(peers[k][self.rank] for k in range(3)))
-                self._peers.append(peers)
+                        dest[k].append(v[k])
+                self.sets.append(local)
+                self._dest.append(dest)
             torch.cuda.synchronize(dev)
         dist.barrier(group=group)
         self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._cur = -1
 
     def arm(self, k):
-        """Direct the next rollout's exchange at buffer set k % n_sets; returns that set."""
+        """Direct the next rollout's exchange at buffer set k % n_sets."""
         self._cur = k % len(self.sets)
-        pr, pd, pi = self._peers[self._cur]
+        pr, pd, pi = self._dest[self._cur]
         self.engine.set_peers(self.rank, self.t_max, pr, pd, pi)
-        return self.sets[self._cur]
 
     def complete(self):
         """Order all ranks' rollout kernels before the gathered buffers are read (stream-ordered).
-        Returns (rew [W,Tmax,E,A], done [W,Tmax,E], info [W,Tmax,E,2]) of the armed set."""
+        On a receiving rank returns (rew [W,E,Tmax,A], done [W,E,Tmax], info [W,E,Tmax,2]) of the
+        armed set (slot r = rank r's envs); None elsewhere."""
         dist.all_reduce(self._flag, group=self.group)
         return self.sets[self._cur]
 
@@ -216,4 +227,4 @@ class PeerGather(object):
             dist.barrier(group=self.group)
             for q in self._own:
                 self._L.madrl_ipc_free(q)
-        self._opened, self._own, self._peers, self.sets = [], [], [], []
+        self._opened, self._own, self._dest, self.sets = [], [], [], []

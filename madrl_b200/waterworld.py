@@ -123,8 +123,9 @@ class BatchedMAWaterWorld(object):
         _lib.check(self._L.madrl_ww_set_launch(self._h, warps_per_block, blocks_per_sm))
 
     def set_peers(self, rank, t_max, rew_peers, done_peers, info_peers):
-        """Enable the fused exchange: `*_peers` are lists (one per rank, this rank included) of
-        tensors aliasing every rank's gather buffers (see madrl_b200.dist.PeerGather)."""
+        """Enable the fused exchange: `*_peers` are lists (one per DESTINATION rank) of tensors
+        aliasing the destination gather buffers; this rank writes slot `rank` of each
+        (see madrl_b200.dist.PeerGather)."""
         n = len(rew_peers)
         arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
         self._peer_keepalive = (rew_peers, done_peers, info_peers)

@@ -18,26 +18,34 @@ def _worker(rank, world, port, q):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        E, T, Np = 96, 12, 5
+        E, T, Np = 96, 45, 5       # T not a multiple of the 6- and 32-step staging runs
         eng = BatchedMAWaterWorld(E, Np, 5, device=dev, seed=9, env_id_base=rank * E, n_coop=1, radius=0.04)
         eng.reset()
-        pg = PeerGather(eng, T, Np)
         ok = True
-        for k in range(3):                                  # exercises both buffer sets
-            act = torch.randn(T, E, Np, 2, device=dev, generator=torch.Generator(dev).manual_seed(100 * k + rank)) * 0.7
-            pg.arm(k)
-            obs, rew, done, info = eng.rollout(act, auto_reset=True)
-            g_rew, g_done, g_info = pg.complete()
-            torch.cuda.synchronize()
-            # reference exchange: plain NCCL all_gather of the local outputs
-            r_rew = torch.empty((world,) + tuple(rew.shape), device=dev)
-            dist.all_gather_into_tensor(r_rew.view(world * T, E, Np), rew)
-            r_info = torch.empty((world,) + tuple(info.shape), dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(r_info.view(world * T, E, 2), info)
-            r_done = torch.empty((world,) + tuple(done.shape), dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(r_done.view(world * T, E), done)
-            ok = ok and torch.equal(g_rew, r_rew) and torch.equal(g_info, r_info) and torch.equal(g_done, r_done)
-        pg.close()
+        for mode in ("root", "all"):
+            pg = PeerGather(eng, T, Np, mode=mode)
+            for k in range(3):                                  # exercises both buffer sets
+                act = torch.randn(T, E, Np, 2, device=dev,
+                                  generator=torch.Generator(dev).manual_seed(100 * k + rank)) * 0.7
+                pg.arm(k)
+                obs, rew, done, info = eng.rollout(act, auto_reset=True)
+                got = pg.complete()
+                torch.cuda.synchronize()
+                # reference exchange: plain NCCL all_gather of the local outputs
+                r_rew = torch.empty((world,) + tuple(rew.shape), device=dev)
+                dist.all_gather_into_tensor(r_rew.view(world * T, E, Np), rew)
+                r_info = torch.empty((world,) + tuple(info.shape), dtype=torch.int32, device=dev)
+                dist.all_gather_into_tensor(r_info.view(world * T, E, 2), info)
+                r_done = torch.empty((world,) + tuple(done.shape), dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(r_done.view(world * T, E), done)
+                if got is not None:                         # env-major [W,E,T,..] -> time-major [W,T,E,..]
+                    g_rew, g_done, g_info = got
+                    ok = ok and torch.equal(g_rew.permute(0, 2, 1, 3), r_rew) and \
+                        torch.equal(g_info.permute(0, 2, 1, 3), r_info) and \
+                        torch.equal(g_done.permute(0, 2, 1), r_done)
+                else:
+                    ok = ok and mode == "root" and rank != 0
+            pg.close()
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
