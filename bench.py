@@ -188,9 +188,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--gather-obs", action="store_true",
                     help="also all-gather the full obs tensor every rollout (NVLink-bound)")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "fused-all", "nccl"],
-                    help="multi-GPU trajectory exchange: fused NVLink peer stores in the rollout kernel "
-                         "(gather to rank 0, or to every rank), or one packed NCCL all_gather")
+    ap.add_argument("--exchange", default="overlap", choices=["overlap", "nccl", "fused", "fused-all"],
+                    help="multi-GPU per-rollout trajectory exchange (see the comment in main())")
     ap.add_argument("--wpb", type=int, default=0)
     ap.add_argument("--bps", type=int, default=0)
     a = ap.parse_args()
@@ -251,51 +250,71 @@ def main():
     n_act = min(a.steps, 4)
     actions = [make_actions(a.workload, T, E, dev, g) for _ in range(n_act)]
     from madrl_b200.dist import PackedTrajectory
-    # rewards / dones / infos of a rollout live in ONE contiguous buffer -> a single collective
     info_w = 1 if WL["family"] == "pe" else 2
+    # Multi-GPU exchange of the per-rollout trajectory tensors (rewards / dones / infos; obs stays
+    # sharded with the data-parallel learner unless --gather-obs):
+    #   overlap (default) one copy-engine P2P copy of the packed buffer to rank 0 over NVLink on a side
+    #                     stream + a completion all-reduce, overlapping the next rollout
+    #                     (madrl_b200.dist.AsyncRootGather)
+    #   nccl              one packed NCCL all_gather after each rollout (serialised with compute)
+    #   fused / fused-all the rollout kernel itself stores the rows into rank 0's / every rank's
+    #                     buffers over NVLink peer memory (madrl_b200.dist.PeerGather)
+    mode, note = ("none" if world == 1 else a.exchange), None
+    peer = agather = None
+    if world > 1 and mode in ("overlap", "fused", "fused-all"):
+        from madrl_b200.dist import AsyncRootGather, PeerGather
+        try:   # every rank must take the same branch: agree on success with an all-reduce
+            if mode == "overlap":
+                agather = AsyncRootGather(T, E, Np, info_w, dev)
+            elif WL["family"] == "ww":
+                peer = PeerGather(eng, T, Np, mode="all" if mode == "fused-all" else "root")
+            else:
+                raise RuntimeError("fused exchange is implemented for Waterworld only")
+            okf = torch.ones(1, device=dev)
+        except Exception as ex:   # e.g. no peer access between the GPUs of this box
+            peer = agather = None
+            note, okf = "%s unavailable (%s)" % (mode, type(ex).__name__), torch.zeros(1, device=dev)
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        if okf.item() == 0:
+            for x in (peer, agather):
+                if x is not None:
+                    x.close()
+            peer = agather = None
+            mode, note = "nccl", note or "peer-memory exchange unavailable on another rank"
     packed = PackedTrajectory(T, E, Np, info_w, dev)
-    out = (torch.empty((T, E, Np, D), device=dev), packed.rew, packed.done, packed.info)
+    obs_buf = torch.empty((T, E, Np, D), device=dev)
+    out = (obs_buf, packed.rew, packed.done, packed.info)
     g_obs = None
     if world > 1 and a.gather_obs:
         g_obs = torch.empty((world * T, E, Np, D), device=dev)
-
-    # Multi-GPU exchange of the per-rollout trajectory tensors (rewards / dones / infos; obs stays
-    # sharded with the data-parallel learner unless --gather-obs).  Default for Waterworld: FUSED --
-    # the rollout kernel stores those rows into every rank's gather buffers over NVLink peer memory
-    # (madrl_b200.dist.PeerGather) and only a tiny completion all-reduce remains; --exchange nccl
-    # uses one packed NCCL all_gather after the kernel instead.
-    peer, peer_note = None, None
-    if world > 1 and a.exchange != "nccl" and WL["family"] == "ww":
-        from madrl_b200.dist import PeerGather
-        try:   # every rank must take the same branch: agree on success with an all-reduce
-            peer = PeerGather(eng, T, Np, mode="all" if a.exchange == "fused-all" else "root")
-            okf = torch.ones(1, device=dev)
-        except Exception as ex:   # e.g. no peer access between the GPUs of this box
-            peer, peer_note, okf = None, "fused exchange unavailable (%s)" % type(ex).__name__, torch.zeros(1, device=dev)
-        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
-        if okf.item() == 0 and peer is not None:
-            peer.close()
-            peer, peer_note = None, "fused exchange unavailable on another rank"
     step_counter = [0]
 
-    def pre_rollout():
-        if peer is not None:
-            peer.arm(step_counter[0])
-            step_counter[0] += 1
-
-    def exchange():
-        if world > 1:
+    def run_rollout(i):
+        k = step_counter[0]
+        step_counter[0] += 1
+        if agather is not None:
+            agather.before_reuse(k)
+            rew_b, done_b, info_b = agather.buffers(k)
+            eng.rollout(actions[i % n_act], auto_reset=True, out=(obs_buf, rew_b, done_b, info_b))
+        else:
             if peer is not None:
+                peer.arm(k)
+            eng.rollout(actions[i % n_act], auto_reset=True, out=out)
+        return k
+
+    def exchange(k):
+        if world > 1:
+            if agather is not None:
+                agather.submit(k)
+            elif peer is not None:
                 peer.complete()
             else:
                 packed.gather_raw()
             if a.gather_obs:
-                dist.all_gather_into_tensor(g_obs, out[0])
+                dist.all_gather_into_tensor(g_obs, obs_buf)
 
     def one_step(i):
-        pre_rollout()
-        eng.rollout(actions[i % n_act], auto_reset=True, out=out)
-        exchange()
+        exchange(run_rollout(i))
 
     def barrier():
         if world > 1:
@@ -314,11 +333,12 @@ def main():
     barrier()
     ev0.record()
     for i in range(a.steps):
-        pre_rollout()
         kev[i][0].record()
-        eng.rollout(actions[i % n_act], auto_reset=True, out=out)
+        k_ = run_rollout(i)
         kev[i][1].record()
-        exchange()
+        exchange(k_)
+    if agather is not None:   # the timed region ends when the last exchange has landed
+        torch.cuda.current_stream(dev).wait_stream(agather.comm)
     ev1.record()
     barrier()
     launches = launch_count() - l0
@@ -334,8 +354,9 @@ def main():
             eng.rollout(actions[i % n_act], auto_reset=True, out=out)
             i += 1
         torch.cuda.synchronize()
-    if peer is not None:
-        peer.close()
+    for x in (peer, agather):
+        if x is not None:
+            x.close()
     kern_ms = float(np.mean([s.elapsed_time(e) for s, e in kev]))
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -391,13 +412,16 @@ def main():
                    "actions": ("uniform {0..4}" if WL["family"] == "pe" else "0.5*N(0,1)") + ", HBM-resident",
                    "l2": "outputs per launch (%.0f MB) exceed L2" % (out[0].numel() * 4 / 1e6),
                    "parallelism": "env-shard x%d" % world,
-                   "gather": "none" if world == 1 else (
-                       ("rew/done/info rows stored by the rollout kernel into %s gather buffers over NVLink "
-                        "peer memory + 1 completion all-reduce per rollout"
-                        % ("every rank's" if a.exchange == "fused-all" else "rank 0's") if peer is not None else
-                        "one packed NCCL all_gather of rew/done/info per rollout" +
-                        (" [%s]" % peer_note if peer_note else "")) +
-                       (" + obs all_gather" if a.gather_obs else ""))},
+                   "gather": {"none": "none",
+                              "overlap": "packed rew/done/info copied to rank 0 over NVLink by the copy engines on "
+                                         "a side stream + 1 completion all-reduce per rollout, overlapped with the "
+                                         "next rollout",
+                              "nccl": "one packed NCCL all_gather of rew/done/info per rollout",
+                              "fused": "rew/done/info rows stored by the rollout kernel into rank 0's gather "
+                                       "buffers over NVLink peer memory + 1 completion all-reduce per rollout",
+                              "fused-all": "rew/done/info rows stored by the rollout kernel into every rank's "
+                                           "gather buffers over NVLink peer memory + 1 completion all-reduce"}[mode]
+                             + (" [%s]" % note if note else "") + (" + obs all_gather" if a.gather_obs else "")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch: 1.0890 GB measured for

@@ -228,3 +228,87 @@ class PeerGather(object):
             for q in self._own:
                 self._L.madrl_ipc_free(q)
         self._opened, self._own, self._dest, self.sets = [], [], [], []
+
+
+class AsyncRootGather(object):
+    """Per-rollout gather of the packed reward / done / info buffers to a root rank that OVERLAPS
+    with the next rollout: after rollout k every rank enqueues, on a side stream, ONE device-to-device
+    copy of its packed buffer into its slot of the root's (CUDA-IPC mapped) gather buffer -- a copy
+    engine transfer over NVLink that uses no SMs, so the persistent rollout kernel of step k+1 runs
+    undisturbed -- followed by one tiny completion all-reduce.  This is the reference's
+    "workers return their paths to the master" (rllab/rllab/sampler/stateful_pool.py:102-157) as a
+    B200 NVLink pattern.  Local buffers and root buffers are double-buffered.
+    """
+
+    def __init__(self, T, n_envs, n_agents, info_width, device, rew_dtype=torch.float32, root=0,
+                 n_sets=2, group=None):
+        import ctypes as C
+        from . import _lib
+        assert dist.is_initialized()
+        self._L = _lib.lib()
+        self.group, self.root, self.device = group, root, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.local = [PackedTrajectory(T, n_envs, n_agents, info_width, device, rew_dtype) for _ in range(n_sets)]
+        nb = self.local[0].nbytes
+        self._slots, self._own, self._opened, self.root_bufs = [], [], [], []
+        with torch.cuda.device(device):
+            for _ in range(n_sets):
+                ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+                if self.rank == root:
+                    _lib.check(self._L.madrl_ipc_alloc(self.world * nb, C.byref(ptr), handle))
+                    self._own.append(ptr.value)
+                everyone = [None] * self.world
+                dist.all_gather_object(everyone, handle.raw if self.rank == root else None, group=group)
+                if self.rank == root:
+                    base = ptr.value
+                else:
+                    q = C.c_void_p()
+                    _lib.check(self._L.madrl_ipc_open(everyone[root], C.byref(q)))
+                    self._opened.append(q.value)
+                    base = q.value
+                whole = torch.as_tensor(_DevBuf(base, self.world * nb), device=device)
+                self.root_bufs.append(whole if self.rank == root else None)
+                self._slots.append(whole[self.rank * nb:(self.rank + 1) * nb])
+            torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+        self.comm = torch.cuda.Stream(device=device)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self._ev = [torch.cuda.Event() for _ in range(n_sets)]
+
+    def buffers(self, k):
+        """(rew, done, info) views the rollout k must write into."""
+        p = self.local[k % len(self.local)]
+        return p.rew, p.done, p.info
+
+    def submit(self, k):
+        """Enqueue the exchange of rollout k (already launched on the current stream)."""
+        i = k % len(self.local)
+        self._ev[i].record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self._ev[i])
+            self._slots[i].copy_(self.local[i].buf, non_blocking=True)     # copy engine, NVLink P2P
+            dist.all_reduce(self._flag, group=self.group)                 # completion ordering
+            self._ev[i].record(self.comm)
+
+    def before_reuse(self, k):
+        """Make the current stream wait until the exchange that last used buffer set k%n is done."""
+        torch.cuda.current_stream(self.device).wait_event(self._ev[k % len(self.local)])
+
+    def result(self, k):
+        """On the root: [W, nbytes] uint8 view of the gathered packed buffers of rollout k (after
+        `before_reuse(k)` / a synchronize); unpack with PackedTrajectory offsets.  None elsewhere."""
+        if self.rank != self.root:
+            return None
+        return self.root_bufs[k % len(self.local)].view(self.world, self.local[0].nbytes)
+
+    def close(self):
+        self.comm.synchronize()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            for q in self._opened:
+                self._L.madrl_ipc_close(q)
+            dist.barrier(group=self.group)
+            for q in self._own:
+                self._L.madrl_ipc_free(q)
+        self._opened, self._own = [], []
