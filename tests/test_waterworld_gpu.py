@@ -47,12 +47,13 @@ CFGS = {
                                     addid=False, obstacle_loc=None),
     "c4": dict(n_pursuers=20, n_evaders=50, n_poison=50),
     "k40": dict(n_pursuers=4, n_evaders=40, n_poison=3, n_sensors=40, n_coop=2, radius=0.03),
+    "big200": dict(n_pursuers=6, n_evaders=120, n_poison=74, n_coop=2, radius=0.02),   # 8 objects per lane
 }
 
 
 @pytest.mark.parametrize("name,E,T", [("c2", 48, 150), ("dense", 32, 150),
                                       ("global_nospeed_randobst", 40, 200), ("c4", 8, 30),
-                                      ("k40", 8, 60)])
+                                      ("k40", 8, 60), ("big200", 3, 25)])
 def test_fp64_trajectories_match_oracle(name, E, T):
     cfg = CFGS[name]
     seed, base = 1234, 1000
