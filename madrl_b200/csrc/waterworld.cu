@@ -108,6 +108,12 @@ __device__ __noinline__ Spawn<real> spawn_object(uint64_t seed, uint32_t env_id,
 // OPL = objects per lane (ceil(n_obj / 32)); KCH = sensors per lane (ceil(K / 32));
 // KC = compile-time sensor count (0 = runtime p.K): with KC known the 7 feature-row stores of a
 // pursuer use immediate offsets from one running pointer instead of 64-bit address arithmetic.
+#ifndef MADRL_WW_NO_JD_SHFL
+#define MADRL_WW_NO_JD_SHFL 0    // 1: recompute the candidate's d2 instead of a third shuffle (experiment)
+#endif
+#ifndef MADRL_WW_MERGED_SCAN
+#define MADRL_WW_MERGED_SCAN 0   // 1: single candidate loop with a uniform class branch (experiment)
+#endif
 #ifndef MADRL_WW_MINBLOCKS_OPL4
 #define MADRL_WW_MINBLOCKS_OPL4 7   // resident 128-thread blocks per SM requested for 65..128 objects
 #endif
@@ -279,6 +285,28 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
             hitE |= hb & mE[c];
             hitP |= hb & mP[c];
             // lanes as SENSORS: scan the surviving candidates of this chunk, ascending index
+#if MADRL_WW_MERGED_SCAN
+            // one loop over all candidates; the class of candidate j is warp-uniform
+            for (unsigned m = cm; m != 0u; m &= m - 1u) {
+              const int j = __ffs(m) - 1;
+              const real jx = __shfl_sync(FULL_MASK, rx, j), jy = __shfl_sync(FULL_MASK, ry, j);
+#if MADRL_WW_NO_JD_SHFL
+              const real jd = jx * jx + jy * jy;
+#else
+              const real jd = __shfl_sync(FULL_MASK, d2, j);
+#endif
+              const int idx = j + 32 * c;
+              const unsigned bit = 1u << j;
+#pragma unroll
+              for (int kc = 0; kc < KCH; ++kc) {
+                const real sv = sx_l[kc] * jx + sy_l[kc] * jy;
+                const bool ok = !((sv < (real)0) | (sv > p.range) | (jd - sv * sv > p.r_p2));
+                if (bit & mE[c])      { if (ok && sv < bE[kc]) { bE[kc] = sv; iE[kc] = idx; } }
+                else if (bit & mP[c]) { if (ok && sv < bP[kc]) { bP[kc] = sv; iP[kc] = idx; } }
+                else                  { if (ok && sv < bU[kc]) { bU[kc] = sv; iU[kc] = idx; } }
+              }
+            }
+#else
 #pragma unroll
             for (int kc = 0; kc < KCH; ++kc) {
               const real sx = sx_l[kc], sy = sy_l[kc];
@@ -296,6 +324,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
               MADRL_WW_SCAN(mP[c], bP[kc], iP[kc])
 #undef MADRL_WW_SCAN
             }
+#endif
           }
 #pragma unroll
           for (int kc = 0; kc < KCH; ++kc) {
