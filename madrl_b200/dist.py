@@ -101,7 +101,7 @@ class PackedTrajectory(object):
 
     def gather(self, group=None):
         """ONE all_gather of the packed buffer; returns (rew, done, info) with a leading rank axis
-        ([W, T, E_local, ...] views, no copies)."""
+        ([W, T, E_local, ...], unpacked copies of the per-rank slices)."""
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
             return self.rew.unsqueeze(0), self.done.unsqueeze(0), self.info.unsqueeze(0)
         world = dist.get_world_size(group)
