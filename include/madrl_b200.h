@@ -1,8 +1,8 @@
 /* madrl_b200 -- C ABI of the B200 batched multi-agent environment engine.
  *
- * One handle = E independent environment instances of one family, held struct-of-arrays in
- * HBM and stepped in lockstep by sm_100a CUDA kernels.  Every entry point replaces, for a whole
- * batch, one method of the reference's Python environment interface
+ * One handle = E independent environment instances of one family, resident in HBM (one
+ * struct-of-arrays record per env) and stepped in lockstep by sm_100a CUDA kernels.  Every entry
+ * point replaces, for a whole batch, one method of the reference's Python environment interface
  * (`madrl_environments/__init__.py:27-119`, AbstractMAEnv):
  *
  *   madrl_ww_*      <-> MAWaterWorld            madrl_environments/pursuit/waterworld.py
@@ -23,7 +23,7 @@
  *     `_host` variants take host pointers and perform the host<->device copies themselves.
  *   - the per-env state lives in one device blob.  The caller may provide it
  *     (`state_dev`, size from `*_state_layout`) or pass NULL to let the library cudaMalloc it.
- *     The layout (byte offsets of the struct-of-arrays fields, env index minor) is reported by
+ *     The layout (byte offsets of the per-env records and constant tables) is reported by
  *     `*_state_layout` so that parity harnesses and `set_param_values`-style callers can read
  *     and write state directly.
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  One handle is used

@@ -2,9 +2,9 @@
 
 Drop-in for the ``reset()/step()`` rollout hot path of sisl/MADRL's ``MAWaterWorld``,
 ``PursuitEvade`` and ``ContinuousHostageWorld`` (``madrl_environments``): E independent env
-instances live struct-of-arrays in HBM and are stepped in lockstep by hand-written sm_100a CUDA
-kernels behind the C ABI in ``include/madrl_b200.h``.  There is no CPU fallback: the classes
-below raise ``EngineError`` if the CUDA library is missing.
+instances live in HBM (one struct-of-arrays record per env) and are stepped in lockstep by
+hand-written sm_100a CUDA kernels behind the C ABI in ``include/madrl_b200.h``.  There is no CPU
+fallback: the classes below raise ``EngineError`` if the CUDA library is missing.
 """
 from ._lib import EngineError, launch_count  # noqa: F401
 from .core import Agent, AbstractMAEnv, EzPickle  # noqa: F401
