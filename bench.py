@@ -424,10 +424,10 @@ def main():
                              + (" [%s]" % note if note else "") + (" + obs all_gather" if a.gather_obs else "")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum per launch: 1.0890 GB measured for
-                     # one E=4096, T=64 launch (ncu --set full, profiles/r1_ww_kernel_final_full.md),
-                     # i.e. 17.0 MB per lockstep step, scaled to this launch's T
-                     "traffic": (1.0890e9 / 64 * T if (E == 4096 and a.workload == "waterworld") else None),
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch: 4.470 GB written +
+                     # 0.067 GB read measured for one E=4096, T=256 launch (ncu --set full,
+                     # profiles/r1_ww_kernel_final_full.md), i.e. 17.7 MB per lockstep step, scaled by T
+                     "traffic": (4.5374e9 / 256 * T if (E == 4096 and a.workload == "waterworld") else None),
                      "traffic_unit": "bytes per launch (algorithmic: %d)" % (bpe * E * T),
                      "peak_kind": peak_kind,
                      "kernel": {"ww": "ww_kernel<float>", "pe": "pe_kernel", "hw": "hw_kernel<float>"}[WL["family"]],
