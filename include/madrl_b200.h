@@ -252,6 +252,13 @@ int madrl_frame_stack_f32(int T, int E, int A, int D, int B, const float* obs_de
 int madrl_standardize_f32(int T, size_t n, float* x_dev, double* mean_dev, double* var_dev,
                           double alpha, double eps, int center, double scale, int enable,
                           void* stream);
+/* DiagnosticsWrapper episode statistics (madrl_environments/__init__.py:314-369): rew [T][E][A],
+ * done uint8 [T][E]; carry float64 [E][A+3] (zero-initialised by the caller, kept between calls);
+ * outputs at the steps where an episode closes (ep_end[t][e] = 1; zeros elsewhere):
+ * ep_reward [T][E][A], ep_disc [T][E] (discounted return of the agent-mean reward), ep_len [T][E]. */
+int madrl_episode_stats_f32(int T, int E, int A, const float* rew_dev, const uint8_t* done_dev,
+                            double discount, int max_traj_len, double* carry_dev, float* ep_reward_dev,
+                            float* ep_disc_dev, int32_t* ep_len_dev, uint8_t* ep_end_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -94,9 +94,64 @@ __global__ void standardize_kernel(int T, size_t n, float* __restrict__ x, doubl
   var[i] = v;
 }
 
+// DiagnosticsWrapper episode statistics (madrl_environments/__init__.py:314-369): per env, walk the
+// time axis accumulating the per-agent episode reward, the episode length and the discounted return
+// of the agent-mean reward; an episode closes where done[t] is set or its length reaches
+// max_traj_len (the wrapper then restarts its counters even though the env goes on).
+// carry [E][A+3] doubles: episode reward per agent, length, discounted return, discount power.
+__global__ void episode_stats_kernel(int T, int E, int A, const float* __restrict__ rew,
+                                     const uint8_t* __restrict__ done, double discount, int max_traj_len,
+                                     double* __restrict__ carry, float* __restrict__ ep_reward,
+                                     float* __restrict__ ep_disc, int32_t* __restrict__ ep_len,
+                                     uint8_t* __restrict__ ep_end) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  double* c = carry + (size_t)e * (A + 3);
+  double len = c[A], disc = c[A + 1], pw = c[A + 2];
+  if (len == 0.0) pw = 1.0;
+  for (int t = 0; t < T; ++t) {
+    const size_t k = ((size_t)t * E + e);
+    double mean = 0.0;
+    for (int a = 0; a < A; ++a) {
+      const double r = (double)rew[k * A + a];
+      c[a] += r;                                              // _episode_reward += rewardlist
+      mean += r;
+    }
+    mean /= (double)A;
+    disc += mean * pw;                                        // _discount_sum of the agent-mean reward
+    pw *= discount;
+    len += 1.0;
+    const bool end = done[k] != 0 || len >= (double)max_traj_len;   // __init__.py:352
+    ep_end[k] = end ? 1 : 0;
+    ep_len[k] = end ? (int32_t)len : 0;
+    ep_disc[k] = end ? (float)disc : 0.0f;
+    for (int a = 0; a < A; ++a) ep_reward[k * A + a] = end ? (float)c[a] : 0.0f;
+    if (end) {
+      for (int a = 0; a < A; ++a) c[a] = 0.0;
+      len = 0.0; disc = 0.0; pw = 1.0;
+    }
+  }
+  c[A] = len; c[A + 1] = disc; c[A + 2] = pw;
+}
+
 }  // namespace madrl
 
 using namespace madrl;
+
+extern "C" int madrl_episode_stats_f32(int T, int E, int A, const float* rew_dev, const uint8_t* done_dev,
+                                       double discount, int max_traj_len, double* carry_dev,
+                                       float* ep_reward_dev, float* ep_disc_dev, int32_t* ep_len_dev,
+                                       uint8_t* ep_end_dev, void* stream) {
+  MADRL_REQUIRE(T >= 1 && E >= 1 && A >= 1 && max_traj_len >= 1, "bad sizes");
+  MADRL_REQUIRE(rew_dev && done_dev && carry_dev && ep_reward_dev && ep_disc_dev && ep_len_dev && ep_end_dev,
+                "NULL buffer");
+  episode_stats_kernel<<<(unsigned)((E + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      T, E, A, rew_dev, done_dev, discount, max_traj_len, carry_dev, ep_reward_dev, ep_disc_dev, ep_len_dev,
+      ep_end_dev);
+  g_launches.fetch_add(1);
+  MADRL_CUDA_CHECK(cudaGetLastError());
+  return MADRL_OK;
+}
 
 extern "C" int madrl_gae_f32(int T, int E, int A, const float* rew_dev, const float* value_dev,
                              const uint8_t* done_dev, const float* last_value_dev, double discount,

@@ -104,6 +104,34 @@ class Standardizer(object):
         return rew
 
 
+class EpisodeStats(object):
+    """DiagnosticsWrapper's per-episode statistics for a whole env batch
+    (madrl_environments/__init__.py:314-369): episode reward per agent, its agent-mean, the
+    discounted return of the agent-mean reward and the episode length, emitted at the steps where
+    an episode closes (``done`` or ``max_traj_len`` reached)."""
+
+    def __init__(self, n_envs, n_agents, device, discount=0.99, max_traj_len=500):
+        self.n_envs, self.n_agents, self.discount, self.max_traj_len = n_envs, n_agents, discount, max_traj_len
+        self.carry = torch.zeros((n_envs, n_agents + 3), dtype=torch.float64, device=device)
+
+    def rollout(self, rew, done):
+        """rew [T,E,A] float32, done [T,E] uint8 -> dict(end [T,E] bool, episode_reward [T,E,A],
+        episode_avg_reward [T,E], episode_disc_return [T,E], episode_length [T,E])."""
+        rew, done = rew.contiguous(), done.contiguous()
+        T, E, A = rew.shape
+        dev = rew.device
+        ep_r = torch.empty((T, E, A), dtype=torch.float32, device=dev)
+        ep_d = torch.empty((T, E), dtype=torch.float32, device=dev)
+        ep_l = torch.empty((T, E), dtype=torch.int32, device=dev)
+        ep_e = torch.empty((T, E), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().madrl_episode_stats_f32(T, E, A, _ptr(rew), _ptr(done), float(self.discount),
+                                                          int(self.max_traj_len), _ptr(self.carry), _ptr(ep_r),
+                                                          _ptr(ep_d), _ptr(ep_l), _ptr(ep_e), _stream(dev)))
+        return dict(end=ep_e.bool(), episode_reward=ep_r, episode_avg_reward=ep_r.mean(dim=-1),
+                    episode_disc_return=ep_d, episode_length=ep_l)
+
+
 def to_paths(obs, actions, rew, done, infos=None):
     """Split time-major rollout arrays [T,E,A,...] (numpy or cpu tensors) into rllab-style paths:
     one dict per (env, agent, episode) with ``observations/actions/rewards/env_infos`` arrays, the

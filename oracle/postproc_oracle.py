@@ -83,3 +83,20 @@ class StandardizeEnv(object):
             self.rew_var = (1 - self.ra) * self.rew_var + self.ra * np.square(r - self.rew_mean)
             r = r / (np.sqrt(self.rew_var) + self.eps)
         return self.scale_reward * r
+
+
+def episode_stats_env(rew, done, discount=0.99, max_traj_len=500):
+    """DiagnosticsWrapper (madrl_environments/__init__.py:314-369) on one env's rollout arrays
+    rew [T, A], done [T]: list of (t, episode_reward [A], avg, disc_return, length) records."""
+    A = rew.shape[1]
+    ep_reward, length, all_rewards, out = np.zeros(A), 0, [], []
+    for t in range(rew.shape[0]):
+        ep_reward += np.asarray(rew[t], dtype=np.float64)
+        length += 1
+        all_rewards.append(np.asarray(rew[t], dtype=np.float64))
+        if done[t] or length >= max_traj_len:                      # __init__.py:352
+            arr = np.asarray(all_rewards).mean(axis=1)
+            disc = np.sum(arr * (discount ** np.arange(len(arr))))   # _discount_sum, __init__.py:392
+            out.append((t, ep_reward.copy(), float(np.mean(ep_reward)), float(disc), length))
+            ep_reward, length, all_rewards = np.zeros(A), 0, []
+    return out

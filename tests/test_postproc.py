@@ -3,7 +3,7 @@ CUDA kernels vs oracle (GPU)."""
 import numpy as np
 import pytest
 
-from oracle.postproc_oracle import StandardizeEnv, discount_cumsum, frame_stack_env, gae_env
+from oracle.postproc_oracle import StandardizeEnv, discount_cumsum, episode_stats_env, frame_stack_env, gae_env
 
 
 class ScriptedEnv(object):
@@ -62,6 +62,37 @@ def test_oracles_equal_reference_wrappers():
         assert np.array_equal(np.array(sr), mine.rew(rew[t]))
 
 
+@pytest.mark.reference
+def test_episode_stats_oracle_equals_reference_wrapper():
+    from oracle.refshim import install
+    install()
+    import gym.spaces as spaces
+    import madrl_environments as me
+    rs = np.random.RandomState(3)
+    T, A, D = 60, 3, 2
+    obs0, obs, rew = rs.randn(A, D), rs.randn(T, A, D), rs.randn(T, A)
+    done = np.zeros(T, bool)
+    done[[7, 30]] = True
+
+    class Env(ScriptedEnv):
+        def step(self, a):
+            o, r, _, i = ScriptedEnv.step(self, a)
+            return o, np.asarray(r), bool(done[self.t - 1]), i
+    w = me.DiagnosticsWrapper(Env(obs0, obs, rew, spaces), discount=0.9, max_traj_len=12, log_interval=10 ** 9)
+    w.reset()
+    got = []
+    for t in range(T):
+        _, _, _, log = w.step(None)
+        if 'global/episode_length' in log:
+            got.append((t, np.array([log['global/episode_reward_agent%d' % a] for a in range(A)]),
+                        log['global/episode_avg_reward'], log['global/episode_disc_return'],
+                        log['global/episode_length']))
+    mine = episode_stats_env(rew, done, 0.9, 12)
+    assert len(got) == len(mine) >= 5
+    for g, m in zip(got, mine):
+        assert g[0] == m[0] and np.array_equal(g[1], m[1]) and g[2] == m[2] and g[3] == m[3] and g[4] == m[4]
+
+
 def test_gae_oracle_matches_rllab_formulas():
     rs = np.random.RandomState(1)
     T, A = 30, 2
@@ -95,7 +126,7 @@ def test_to_paths_splits_at_done():
 @pytest.mark.gpu
 def test_cuda_postproc_matches_oracle():
     import torch
-    from madrl_b200.postproc import FrameStack, Standardizer, gae
+    from madrl_b200.postproc import EpisodeStats, FrameStack, Standardizer, gae
     rs = np.random.RandomState(2)
     T, E, A, D, B = 50, 7, 3, 11, 4
     obs0 = rs.randn(E, A, D).astype(np.float32)
@@ -139,3 +170,15 @@ def test_cuda_postproc_matches_oracle():
             assert np.abs(m.obs(obs[t, e].astype(np.float64)) - xo[t, e].cpu().numpy()).max() < 1e-5
             assert np.abs(m.rew(rew[t, e].astype(np.float64)) - xr[t, e].cpu().numpy()).max() < 1e-5
         assert np.abs(m.obs_var - sd.obs_var[e].cpu().numpy()).max() < 1e-12
+    # episode statistics (two calls exercise the carry)
+    es = EpisodeStats(E, A, dev, discount=0.9, max_traj_len=12)
+    r_t = torch.as_tensor(rew, device=dev)
+    s1, s2 = es.rollout(r_t[:23], d_t[:23]), es.rollout(r_t[23:], d_t[23:])
+    cat = {k: torch.cat([s1[k], s2[k]]).cpu().numpy() for k in s1}
+    for e in range(E):
+        recs = episode_stats_env(rew[:, e].astype(np.float64), done[:, e], 0.9, 12)
+        assert [r[0] for r in recs] == list(np.nonzero(cat['end'][:, e])[0])
+        for t, ep_r, avg, disc, length in recs:
+            assert np.abs(cat['episode_reward'][t, e] - ep_r).max() < 1e-4
+            assert abs(cat['episode_avg_reward'][t, e] - avg) < 1e-4 and abs(cat['episode_disc_return'][t, e] - disc) < 1e-4
+            assert cat['episode_length'][t, e] == length
