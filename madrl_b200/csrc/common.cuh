@@ -45,8 +45,17 @@ __device__ __forceinline__ double real_inf<double>() {
 }
 
 // Streaming (evict-first) store for write-once trajectory tensors.
+#ifndef MADRL_PLAIN_STORES
+#define MADRL_PLAIN_STORES 0   // 1: ordinary write-back stores instead (experiment)
+#endif
 template <typename T>
-__device__ __forceinline__ void store_stream(T* p, T v) { __stcs(p, v); }
+__device__ __forceinline__ void store_stream(T* p, T v) {
+#if MADRL_PLAIN_STORES
+  *p = v;
+#else
+  __stcs(p, v);
+#endif
+}
 
 // Explicit shared-window accesses on 32-bit shared addresses.  Keeping ONE 32-bit base address
 // in a register (instead of a generic pointer the compiler re-derives from SR_CgaCtaId at every

@@ -84,8 +84,11 @@ __device__ __forceinline__ double numpy_mean(const double* a, int n) {
 
 // EPL = evaders per lane (ceil(Ne/32)); CPL = window cells per lane (ceil(R*R/32));
 // RC = compile-time obs_range (0 = runtime p.R).
+#ifndef MADRL_PE_MINBLOCKS
+#define MADRL_PE_MINBLOCKS 7   // resident 128-thread blocks per SM requested (7 -> 72 registers)
+#endif
 template <int EPL, int CPL, int RC>
-__global__ void __launch_bounds__(128, 7) pe_kernel(const __grid_constant__ PEParams p) {
+__global__ void __launch_bounds__(128, MADRL_PE_MINBLOCKS) pe_kernel(const __grid_constant__ PEParams p) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
