@@ -21,6 +21,7 @@ struct HWParams {
   int E, env_id_base, Nr, Nc, Nh, K, n_coop_save, D, Nall;
   int reward_global, addid, random_key, timestep_limit, max_path_length;
   int T, mode, auto_reset;
+  size_t obs_step, agent_step;   // element strides of one lockstep step: E*Nr*D and E*Nr
   real r_r2, range, cull2;                    // sensing thresholds (hw:66-67)
   real coll2_c, coll2_h, coll2_bomb, coll2_key;  // exact squared collision thresholds (hw:269-296)
   real gate_lo;                               // 0.5 + radius (hw:257)
@@ -90,7 +91,6 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
     sy_l[kc] = (k < K) ? p.sensors[K + k] : (real)0;
   }
   const int n_tail = 5 + (p.addid ? 1 : 0);
-  const size_t step_stride = (size_t)p.E * p.Nr * p.D;
   typedef typename HVec2<real>::type V2;
 
   for (int e = warp_global; e < p.E; e += warp_stride) {
@@ -128,7 +128,7 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
       act.x = 0; act.y = 0;
       if (p.mode == 0 && lane < p.Nr) {
         act = *act_t;
-        if (t + 1 < p.T) prefetch_l1(act_t + (size_t)p.E * p.Nr);   // next step's action -> L1
+        if (t + 1 < p.T) prefetch_l1(act_t + p.agent_step);   // next step's action -> L1
       }
       bool need_reset;
       do {
@@ -382,9 +382,9 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
         }
         pass = need_reset ? 1 : 0;
       } while (need_reset);
-      obs_t += step_stride;
-      act_t += (size_t)p.E * p.Nr;
-      rew_t += (size_t)p.E * p.Nr;
+      obs_t += p.obs_step;
+      act_t += p.agent_step;
+      rew_t += p.agent_step;
       te += (size_t)p.E;
     }
 #pragma unroll
@@ -559,6 +559,7 @@ static int hw_launch(madrl_hostage* h, int mode, int T, const void* actions, voi
   p.reward_global = c.reward_global; p.addid = c.addid; p.random_key = c.random_key;
   p.timestep_limit = c.timestep_limit; p.max_path_length = c.max_path_length;
   p.T = T; p.mode = mode; p.auto_reset = auto_reset;
+  p.obs_step = (size_t)p.E * p.Nr * p.D; p.agent_step = (size_t)p.E * p.Nr;
   const double r = c.radius;                         // rescuers & criminals; hostages 2r (hw:111-120)
   p.r_r2 = (real)(r * r);
   p.range = (real)c.sensor_range;

@@ -31,6 +31,7 @@ struct PEParams {
   int E, env_id_base, Np, Ne, R, off, xs, ys, n_maps, D;
   int n_catch, surround, reward_global, include_id, sample_maps, max_path_length, flatten;
   int T, mode, auto_reset;
+  size_t obs_step, agent_step;    // element strides of one lockstep step: E*Np*D and E*Np
   int smem_per_warp, cells_pad;   // bytes of shared memory per warp; xs*ys rounded up to 32
   double constraint_window, catchr, term_pursuit, urgency;
   float wall_val, one_val;        // float32(1/layer_norm) the two ways the reference gets it
@@ -114,7 +115,6 @@ __global__ void __launch_bounds__(128, MADRL_PE_MINBLOCKS) pe_kernel(const __gri
     wdy[it] = w % R - p.off;
   }
   const int n_tail = p.include_id ? 1 : 0;
-  const size_t step_stride = (size_t)p.E * Np * p.D;
 
   for (int e = warp_global; e < p.E; e += warp_stride) {
     if (p.mode == 1 && p.mask != nullptr && p.mask[e] == 0) continue;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(128, MADRL_PE_MINBLOCKS) pe_kernel(const __gri
       int act = 4;
       if (p.mode == 0 && lane < Np) {
         act = *act_t;
-        if (t + 1 < p.T) prefetch_l1(act_t + (size_t)p.E * Np);   // next step's action -> L1
+        if (t + 1 < p.T) prefetch_l1(act_t + p.agent_step);   // next step's action -> L1
       }
       bool need_reset;
       do {
@@ -376,9 +376,9 @@ __global__ void __launch_bounds__(128, MADRL_PE_MINBLOCKS) pe_kernel(const __gri
         }
         pass = need_reset ? 1 : 0;
       } while (need_reset);
-      obs_t += step_stride;
-      rew_t += (size_t)p.E * Np;
-      act_t += (size_t)p.E * Np;
+      obs_t += p.obs_step;
+      rew_t += p.agent_step;
+      act_t += p.agent_step;
       te += (size_t)p.E;
     }
     // ---- registers / shared memory -> state records ---------------------------------------------
@@ -557,6 +557,7 @@ static int pe_launch(madrl_pursuit* h, int mode, int T, const int32_t* actions, 
   p.include_id = c.include_id; p.sample_maps = c.sample_maps; p.max_path_length = c.max_path_length;
   p.flatten = c.flatten;
   p.T = T; p.mode = mode; p.auto_reset = auto_reset;
+  p.obs_step = (size_t)p.E * p.Np * p.D; p.agent_step = (size_t)p.E * p.Np;
   const int ncell = c.xs * c.ys, RR = c.obs_range * c.obs_range;
   p.cells_pad = (ncell + 31) / 32 * 32;
   p.smem_per_warp = (int)align_up((size_t)p.cells_pad * 4 + (size_t)c.n_pursuers * RR * 2, 16);

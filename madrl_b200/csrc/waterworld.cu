@@ -33,6 +33,9 @@ struct WWParams {
   int E, env_id_base, Np, Ne, Npo, K, n_coop, D, Nall;
   int reward_global, addid, speed_features, random_obstacle, timestep_limit, max_path_length;
   int T, mode, auto_reset;  // mode 0 = rollout, 1 = reset
+  // element strides of one lockstep step in the trajectory tensors (host-computed so that the
+  // per-step pointer bumps are plain 64-bit adds on constant-bank operands)
+  size_t obs_step, agent_step;   // E*Np*D and E*Np
   real r_p2, range, cull2;                           // sensing thresholds (ww:68-69)
   real coll2_e, coll2_po;                            // (r_p + r_obj) as exact squared thresholds
   real obst2_p, obst2_e, obst2_po;                   // (r_class + R_obst)       ww:251,259,267
@@ -152,7 +155,6 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
   }
   const int n_feat = p.speed_features ? 7 : 4;
   const int n_tail = 2 + (p.addid ? 1 : 0);
-  const size_t step_stride = (size_t)p.E * p.Np * p.D;   // obs elements per lockstep step
   typedef typename Vec2<real>::type V2;
 
   for (int e = warp_global; e < p.E; e += warp_stride) {
@@ -197,7 +199,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
       act.x = 0; act.y = 0;
       if (p.mode == 0 && lane < p.Np) {
         act = *act_t;
-        if (t + 1 < p.T) prefetch_l1(act_t + (size_t)p.E * p.Np);   // next step's action -> L1
+        if (t + 1 < p.T) prefetch_l1(act_t + p.agent_step);   // next step's action -> L1
       }
       bool need_reset;
       do {
@@ -464,9 +466,9 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
         }
         pass = need_reset ? 1 : 0;
       } while (need_reset);
-      obs_t += step_stride;
-      act_t += (size_t)p.E * p.Np;
-      rew_t += (size_t)p.E * p.Np;
+      obs_t += p.obs_step;
+      act_t += p.agent_step;
+      rew_t += p.agent_step;
       te += (size_t)p.E;
     }
     if (PEER && p.n_peers > 0 && sc_rew > 0 && lane < sc_rew * p.Np) {   // partial reward run at the end
@@ -686,6 +688,7 @@ static int ww_launch(madrl_ww* h, int mode, int T, const void* actions, void* ob
   p.random_obstacle = c.random_obstacle; p.timestep_limit = c.timestep_limit;
   p.max_path_length = c.max_path_length;
   p.T = T; p.mode = mode; p.auto_reset = auto_reset;
+  p.obs_step = (size_t)p.E * p.Np * p.D; p.agent_step = (size_t)p.E * p.Np;
   // radii ww:108-118 (double arithmetic as in the reference, then narrowed once)
   const double r_p = c.radius, r_e = c.radius * 2, r_po = c.radius * 3 / 4;
   p.r_p2 = (real)(r_p * r_p);
