@@ -263,24 +263,16 @@ def main():
     peer = agather = None
     if world > 1 and mode in ("overlap", "fused", "fused-all"):
         from madrl_b200.dist import AsyncRootGather, PeerGather
-        try:   # every rank must take the same branch: agree on success with an all-reduce
+        try:   # AsyncRootGather agrees on success across ranks internally and raises on ALL ranks
             if mode == "overlap":
                 agather = AsyncRootGather(T, E, Np, info_w, dev)
             elif WL["family"] == "ww":
                 peer = PeerGather(eng, T, Np, mode="all" if mode == "fused-all" else "root")
             else:
                 raise RuntimeError("fused exchange is implemented for Waterworld only")
-            okf = torch.ones(1, device=dev)
         except Exception as ex:   # e.g. no peer access between the GPUs of this box
             peer = agather = None
-            note, okf = "%s unavailable (%s)" % (mode, type(ex).__name__), torch.zeros(1, device=dev)
-        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
-        if okf.item() == 0:
-            for x in (peer, agather):
-                if x is not None:
-                    x.close()
-            peer = agather = None
-            mode, note = "nccl", note or "peer-memory exchange unavailable on another rank"
+            mode, note = "nccl", "%s unavailable (%s)" % (mode, type(ex).__name__)
     packed = PackedTrajectory(T, E, Np, info_w, dev)
     obs_buf = torch.empty((T, E, Np, D), device=dev)
     out = (obs_buf, packed.rew, packed.done, packed.info)

@@ -251,26 +251,42 @@ class AsyncRootGather(object):
         self.local = [PackedTrajectory(T, n_envs, n_agents, info_width, device, rew_dtype) for _ in range(n_sets)]
         nb = self.local[0].nbytes
         self._slots, self._own, self._opened, self.root_bufs = [], [], [], []
+        failure = None
         with torch.cuda.device(device):
             for _ in range(n_sets):
                 ptr, handle = C.c_void_p(), C.create_string_buffer(64)
-                if self.rank == root:
-                    _lib.check(self._L.madrl_ipc_alloc(self.world * nb, C.byref(ptr), handle))
-                    self._own.append(ptr.value)
+                try:
+                    if self.rank == root:
+                        _lib.check(self._L.madrl_ipc_alloc(self.world * nb, C.byref(ptr), handle))
+                        self._own.append(ptr.value)
+                except Exception as ex:          # keep going: every rank must reach the collectives below
+                    failure = failure or ex
                 everyone = [None] * self.world
-                dist.all_gather_object(everyone, handle.raw if self.rank == root else None, group=group)
-                if self.rank == root:
-                    base = ptr.value
-                else:
-                    q = C.c_void_p()
-                    _lib.check(self._L.madrl_ipc_open(everyone[root], C.byref(q)))
-                    self._opened.append(q.value)
-                    base = q.value
-                whole = torch.as_tensor(_DevBuf(base, self.world * nb), device=device)
-                self.root_bufs.append(whole if self.rank == root else None)
-                self._slots.append(whole[self.rank * nb:(self.rank + 1) * nb])
+                dist.all_gather_object(everyone, handle.raw if (self.rank == root and failure is None) else None,
+                                       group=group)
+                try:
+                    if failure is None and everyone[root] is None:
+                        raise RuntimeError("root could not export its gather buffer")
+                    if failure is None:
+                        if self.rank == root:
+                            base = ptr.value
+                        else:
+                            q = C.c_void_p()
+                            _lib.check(self._L.madrl_ipc_open(everyone[root], C.byref(q)))
+                            self._opened.append(q.value)
+                            base = q.value
+                        whole = torch.as_tensor(_DevBuf(base, self.world * nb), device=device)
+                        self.root_bufs.append(whole if self.rank == root else None)
+                        self._slots.append(whole[self.rank * nb:(self.rank + 1) * nb])
+                except Exception as ex:
+                    failure = failure or ex
             torch.cuda.synchronize(device)
-        dist.barrier(group=group)
+        # agree on success: either every rank uses the peer-memory path or none does
+        ok = torch.tensor([0.0 if failure is not None else 1.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok.item() == 0:
+            self._release()
+            raise RuntimeError("AsyncRootGather unavailable: %r" % (failure or "failure on another rank"))
         self.comm = torch.cuda.Stream(device=device)
         self._flag = torch.zeros(1, dtype=torch.int32, device=device)
         self._ev = [torch.cuda.Event() for _ in range(n_sets)]
@@ -301,10 +317,7 @@ class AsyncRootGather(object):
             return None
         return self.root_bufs[k % len(self.local)].view(self.world, self.local[0].nbytes)
 
-    def close(self):
-        self.comm.synchronize()
-        torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)
+    def _release(self):
         with torch.cuda.device(self.device):
             for q in self._opened:
                 self._L.madrl_ipc_close(q)
@@ -312,3 +325,9 @@ class AsyncRootGather(object):
             for q in self._own:
                 self._L.madrl_ipc_free(q)
         self._opened, self._own = [], []
+
+    def close(self):
+        self.comm.synchronize()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        self._release()
