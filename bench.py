@@ -416,10 +416,12 @@ def main():
                              + (" [%s]" % note if note else "") + (" + obs all_gather" if a.gather_obs else "")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum per launch: 4.470 GB written +
-                     # 0.067 GB read measured for one E=4096, T=256 launch (ncu --set full,
-                     # profiles/r1_ww_kernel_final_full.md), i.e. 17.7 MB per lockstep step, scaled by T
-                     "traffic": (4.5374e9 / 256 * T if (E == 4096 and a.workload == "waterworld") else None),
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the ncu --set full
+                     # captures summarised in profiles/r1_{ww,pe,hw}_kernel_final_full.md, expressed per
+                     # env-step (Waterworld C2: 4.537 GB per 4096x256 launch; Pursuit C3: 2.581 GB per
+                     # 65536x8; Hostage C5: 1.637 GB per 8192x32) and scaled to this launch
+                     "traffic": ({"waterworld": 4327.0, "pursuit": 4923.0, "hostage": 6246.0}[a.workload] * E * T
+                                 if a.workload in ("waterworld", "pursuit", "hostage") else None),
                      "traffic_unit": "bytes per launch (algorithmic: %d)" % (bpe * E * T),
                      "peak_kind": peak_kind,
                      "kernel": {"ww": "ww_kernel<float>", "pe": "pe_kernel", "hw": "hw_kernel<float>"}[WL["family"]],
