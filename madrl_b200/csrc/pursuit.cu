@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(128, MADRL_PE_MINBLOCKS) pe_kernel(const __gri
           }
           if (lane < Np) store_stream(rew_t, (float)r);
           // ---- the captured evaders leave the map only now (still visible in this obs) -----------
+          __syncwarp();   // every lane's window reads of the cell words precede the decrements below
           int n_live = 0;
 #pragma unroll
           for (int c = 0; c < EPL; ++c) {
