@@ -260,6 +260,23 @@ int madrl_episode_stats_f32(int T, int E, int A, const float* rew_dev, const uin
                             double discount, int max_traj_len, double* carry_dev, float* ep_reward_dev,
                             float* ep_disc_dev, int32_t* ep_len_dev, uint8_t* ep_end_dev, void* stream);
 
+/* Whole-batch moments, deterministic (fixed grid, fixed combination order), float64 accumulation,
+ * NumPy's two-pass population variance.  Series s0 = a, s1 = b, s2 = b - a (b may be NULL):
+ * stats[0..2] = means, stats[3..5] = variances, stats[6..8] = minima (MADRL_MOMENTS_STATS doubles).
+ * workspace: MADRL_MOMENTS_WS doubles of device scratch.  With a = baseline prediction and
+ * b = returns this gives explained_variance_1d's terms (rllab/rllab/misc/special.py:51-59):
+ * var(y) = stats[4], var(y - ypred) = stats[5], var(ypred) = stats[3]. */
+#define MADRL_MOMENTS_STATS 9
+#define MADRL_MOMENTS_WS 4096
+int madrl_moments_f32(size_t n, const float* a_dev, const float* b_dev, double* stats_dev,
+                      double* workspace_dev, void* stream);
+/* center_advantages / shift_advantages_to_positive (rllab/rllab/algos/util.py:7-12, applied to the
+ * concatenated advantages at rllab/rllab/sampler/base.py:82-86), in place over adv [n]:
+ * center: (x - mean) / (std + 1e-8); positive: (x - min) + 1e-8 (after centring when both).
+ * stats_dev receives the moments of the INPUT as in madrl_moments_f32 (series 0). */
+int madrl_center_advantages_f32(size_t n, float* adv_dev, int center, int positive, double* stats_dev,
+                                double* workspace_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

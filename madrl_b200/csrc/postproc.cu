@@ -134,6 +134,113 @@ __global__ void episode_stats_kernel(int T, int E, int A, const float* __restric
   c[A] = len; c[A + 1] = disc; c[A + 2] = pw;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Whole-batch moments for advantage centring (rllab/rllab/algos/util.py:7-12, applied at
+// rllab/rllab/sampler/base.py:82-86) and explained variance (rllab/rllab/misc/special.py:51-59).
+// NumPy semantics: mean, then the population variance as the mean of squared deviations (two
+// passes), float64 accumulation.  Deterministic: fixed grid, per-block partials combined in a fixed
+// order by one warp (no atomics), so a given input always yields the same bits.
+//
+// Three series are derived per element from (a, b):  s0 = a,  s1 = b,  s2 = b - a  (b optional).
+constexpr int kMomBlocks = 592;          // 4 CTAs x 148 SMs
+constexpr int kMomThreads = 256;
+constexpr int kMomSeries = 3;
+static_assert(kMomBlocks * 2 * kMomSeries <= MADRL_MOMENTS_WS, "workspace too small");
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_down_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// pass 0 (means == nullptr): partial sums and minima; pass 1: partial sums of squared deviations.
+// part [kMomBlocks][2*kMomSeries].
+__global__ void __launch_bounds__(kMomThreads) moments_partial_kernel(size_t n, const float* __restrict__ a,
+                                                                      const float* __restrict__ b,
+                                                                      const double* __restrict__ means,
+                                                                      double* __restrict__ part) {
+  double acc[kMomSeries] = {0.0, 0.0, 0.0};
+  double mn[kMomSeries] = {INFINITY, INFINITY, INFINITY};
+  double mu[kMomSeries] = {0.0, 0.0, 0.0};
+  if (means) {
+#pragma unroll
+    for (int s = 0; s < kMomSeries; ++s) mu[s] = means[s];
+  }
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double va = (double)__ldcs(a + i);
+    const double vb = b ? (double)__ldcs(b + i) : 0.0;
+    const double v[kMomSeries] = {va, vb, vb - va};
+#pragma unroll
+    for (int s = 0; s < kMomSeries; ++s) {
+      if (means) {
+        const double d = v[s] - mu[s];
+        acc[s] += d * d;
+      } else {
+        acc[s] += v[s];
+        mn[s] = fmin(mn[s], v[s]);
+      }
+    }
+  }
+  __shared__ double sh[kMomThreads / 32][2 * kMomSeries];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int s = 0; s < kMomSeries; ++s) {
+    const double t = warp_sum(acc[s]);
+    const double m = warp_min(mn[s]);
+    if (lane == 0) { sh[w][2 * s] = t; sh[w][2 * s + 1] = m; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * kMomSeries) {
+    double r = sh[0][threadIdx.x];
+    for (int k = 1; k < kMomThreads / 32; ++k)
+      r = (threadIdx.x & 1) ? fmin(r, sh[k][threadIdx.x]) : r + sh[k][threadIdx.x];
+    part[(size_t)blockIdx.x * 2 * kMomSeries + threadIdx.x] = r;
+  }
+}
+
+// One warp folds the block partials in a fixed order.  pass 0: stats[s] = mean_s, stats[6+s] = min_s;
+// pass 1: stats[3+s] = var_s (population).
+__global__ void moments_finalize_kernel(size_t n, const double* __restrict__ part, int pass,
+                                        double* __restrict__ stats) {
+  const int lane = threadIdx.x;
+#pragma unroll
+  for (int s = 0; s < kMomSeries; ++s) {
+    double t = 0.0, m = INFINITY;
+    for (int k = lane; k < kMomBlocks; k += 32) {
+      t += part[(size_t)k * 2 * kMomSeries + 2 * s];
+      m = fmin(m, part[(size_t)k * 2 * kMomSeries + 2 * s + 1]);
+    }
+    t = warp_sum(t);
+    m = warp_min(m);
+    if (lane == 0) {
+      if (pass == 0) { stats[s] = t / (double)n; stats[6 + s] = m; }
+      else stats[3 + s] = t / (double)n;
+    }
+  }
+}
+
+// center_advantages: (x - mean) / (std + 1e-8); shift_advantages_to_positive: (x - min) + 1e-8 on the
+// (possibly centred) values, util.py:7-12.
+__global__ void center_apply_kernel(size_t n, float* __restrict__ x, const double* __restrict__ stats,
+                                    int center, int positive) {
+  const double mean = stats[0], sd = sqrt(stats[3]) + 1e-8, mn = stats[6];
+  const double cmin = center ? (mn - mean) / sd : mn;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double v = (double)x[i];
+    if (center) v = (v - mean) / sd;
+    if (positive) v = (v - cmin) + 1e-8;
+    __stcs(x + i, (float)v);
+  }
+}
+
 }  // namespace madrl
 
 using namespace madrl;
@@ -193,4 +300,36 @@ extern "C" int madrl_standardize_f32(int T, size_t n, float* x_dev, double* mean
   g_launches.fetch_add(1);
   MADRL_CUDA_CHECK(cudaGetLastError());
   return MADRL_OK;
+}
+
+static int run_moments(size_t n, const float* a, const float* b, double* stats, double* ws, cudaStream_t s) {
+  moments_partial_kernel<<<kMomBlocks, kMomThreads, 0, s>>>(n, a, b, nullptr, ws);
+  moments_finalize_kernel<<<1, 32, 0, s>>>(n, ws, 0, stats);
+  moments_partial_kernel<<<kMomBlocks, kMomThreads, 0, s>>>(n, a, b, stats, ws);
+  moments_finalize_kernel<<<1, 32, 0, s>>>(n, ws, 1, stats);
+  g_launches.fetch_add(4);
+  MADRL_CUDA_CHECK(cudaGetLastError());
+  return MADRL_OK;
+}
+
+extern "C" int madrl_center_advantages_f32(size_t n, float* adv_dev, int center, int positive,
+                                           double* stats_dev, double* workspace_dev, void* stream) {
+  MADRL_REQUIRE(n >= 1, "bad sizes");
+  MADRL_REQUIRE(adv_dev && stats_dev && workspace_dev, "NULL buffer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rc = run_moments(n, adv_dev, nullptr, stats_dev, workspace_dev, s);
+  if (rc) return rc;
+  if (center || positive) {
+    center_apply_kernel<<<kMomBlocks, kMomThreads, 0, s>>>(n, adv_dev, stats_dev, center, positive);
+    g_launches.fetch_add(1);
+    MADRL_CUDA_CHECK(cudaGetLastError());
+  }
+  return MADRL_OK;
+}
+
+extern "C" int madrl_moments_f32(size_t n, const float* a_dev, const float* b_dev, double* stats_dev,
+                                 double* workspace_dev, void* stream) {
+  MADRL_REQUIRE(n >= 1, "bad sizes");
+  MADRL_REQUIRE(a_dev && stats_dev && workspace_dev, "NULL buffer");
+  return run_moments(n, a_dev, b_dev, stats_dev, workspace_dev, (cudaStream_t)stream);
 }

@@ -4,6 +4,9 @@ right after ``env.step`` in its sampler loop, as streaming passes over ``[T, E, 
 * ``gae``            rllab ``BaseSampler.process_samples`` (rllab/rllab/sampler/base.py:48-68)
 * ``FrameStack``     ``ObservationBuffer`` (madrl_environments/__init__.py:143-196)
 * ``Standardizer``   ``StandardizedEnv``   (madrl_environments/__init__.py:204-291)
+* ``center_advantages`` / ``explained_variance``  the whole-batch statistics of
+                     ``process_samples`` (base.py:69-86; rllab/rllab/algos/util.py:7-12,
+                     rllab/rllab/misc/special.py:51-59)
 * ``to_paths``       the per-agent ``paths`` dicts of ``dec_rollout``
                      (rllab/rllab/sampler/ma_sampler.py:52-100), built on the host from gathered
                      tensors for callers that still want rllab's list-of-paths format.
@@ -38,6 +41,50 @@ def gae(rew, values, done, discount, gae_lambda, last_value=None):
                                             float(discount), float(gae_lambda), _ptr(adv), _ptr(ret),
                                             _stream(rew.device)))
     return adv, ret
+
+
+MOMENTS_STATS, MOMENTS_WS = 9, 4096            # include/madrl_b200.h
+
+
+def _moments_buffers(dev):
+    return (torch.empty(MOMENTS_STATS, dtype=torch.float64, device=dev),
+            torch.empty(MOMENTS_WS, dtype=torch.float64, device=dev))
+
+
+def center_advantages(adv, center=True, positive=False, inplace=False):
+    """``util.center_advantages`` / ``util.shift_advantages_to_positive`` over every sample of the
+    batch (base.py:82-86 applies them to the concatenation of all paths): float64 mean / population
+    std / min computed on the device, deterministic.  Returns the processed tensor (same shape)."""
+    out = adv.contiguous() if inplace else adv.contiguous().clone()
+    stats, ws = _moments_buffers(out.device)
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().madrl_center_advantages_f32(out.numel(), _ptr(out), int(bool(center)),
+                                                          int(bool(positive)), _ptr(stats), _ptr(ws),
+                                                          _stream(out.device)))
+    return out
+
+
+def moments(a, b=None):
+    """float64 [9] cuda tensor: means, population variances and minima of the series a, b, b - a
+    taken over every element (NumPy's two-pass ``var``)."""
+    a = a.contiguous()
+    b = b.contiguous() if b is not None else None
+    assert b is None or b.numel() == a.numel()
+    stats, ws = _moments_buffers(a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().madrl_moments_f32(a.numel(), _ptr(a), _ptr(b), _ptr(stats), _ptr(ws),
+                                                _stream(a.device)))
+    return stats
+
+
+def explained_variance(ypred, y):
+    """``special.explained_variance_1d`` (special.py:51-59) of baseline predictions against returns,
+    over every sample of the batch; one 72-byte device->host read."""
+    st = moments(ypred, y).cpu().numpy()
+    var_pred, vary, var_res = float(st[3]), float(st[4]), float(st[5])
+    if np.isclose(vary, 0):
+        return 0 if var_pred > 0 else 1
+    return 1 - var_res / (vary + 1e-8)
 
 
 class FrameStack(object):

@@ -4,6 +4,8 @@
   (rllab/rllab/sampler/base.py:48-68; ``discount_cumsum`` = rllab/rllab/misc/special.py:107-111),
 * ``ObservationBuffer`` (madrl_environments/__init__.py:143-196),
 * ``StandardizedEnv``   (madrl_environments/__init__.py:204-291),
+* ``center_advantages`` / ``shift_advantages_to_positive`` (rllab/rllab/algos/util.py:7-12) and
+  ``explained_variance_1d`` (rllab/rllab/misc/special.py:51-59),
 
 applied to time-major rollout arrays of ONE env ``[T, A, ...]`` with VecEnvExecutor auto-reset
 semantics (the obs slot of a done step already holds the reset observation).
@@ -100,3 +102,22 @@ def episode_stats_env(rew, done, discount=0.99, max_traj_len=500):
             out.append((t, ep_reward.copy(), float(np.mean(ep_reward)), float(disc), length))
             ep_reward, length, all_rewards = np.zeros(A), 0, []
     return out
+
+
+def center_advantages(adv):                             # rllab/rllab/algos/util.py:7-8
+    adv = np.asarray(adv, dtype=np.float64)
+    return (adv - np.mean(adv)) / (adv.std() + 1e-8)
+
+
+def shift_advantages_to_positive(adv):                  # rllab/rllab/algos/util.py:11-12
+    adv = np.asarray(adv, dtype=np.float64)
+    return (adv - np.min(adv)) + 1e-8
+
+
+def explained_variance_1d(ypred, y):                    # rllab/rllab/misc/special.py:51-59
+    ypred, y = np.asarray(ypred, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    assert y.ndim == 1 and ypred.ndim == 1
+    vary = np.var(y)
+    if np.isclose(vary, 0):
+        return 0 if np.var(ypred) > 0 else 1
+    return 1 - np.var(y - ypred) / (vary + 1e-8)

@@ -139,6 +139,38 @@ def load_reference():
     return MAWaterWorld, PursuitEvade, ContinuousHostageWorld
 
 
+def load_rllab_numeric():
+    """(rllab.algos.util, rllab.misc.special) loaded from their files with the theano / rllab
+    package imports stubbed out -- only their NumPy functions are used (center_advantages,
+    shift_advantages_to_positive, explained_variance_1d, discount_cumsum)."""
+    import importlib.util
+    if not reference_available():
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    saved = dict(sys.modules)
+    try:
+        for name in ("theano", "theano.tensor", "theano.tensor.nnet", "theano.tensor.extra_ops", "rllab",
+                     "rllab.core", "rllab.misc"):
+            _module(name)
+        sys.modules["theano"].tensor = sys.modules["theano.tensor"]
+        sys.modules["theano.tensor"].nnet = sys.modules["theano.tensor.nnet"]
+        sys.modules["theano.tensor"].extra_ops = sys.modules["theano.tensor.extra_ops"]
+        _module("rllab.core.serializable", Serializable=type("Serializable", (object,), {}))
+        _module("rllab.misc.ext", extract=lambda *a, **k: None)
+        out = []
+        for rel, name in (("rllab/rllab/algos/util.py", "_ref_rllab_algos_util"),
+                          ("rllab/rllab/misc/special.py", "_ref_rllab_misc_special")):
+            spec = importlib.util.spec_from_file_location(name, os.path.join(REFERENCE_ROOT, rel))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            out.append(mod)
+        return tuple(out)
+    finally:
+        for k in list(sys.modules):
+            if k not in saved:
+                del sys.modules[k]
+        sys.modules.update(saved)
+
+
 class _NumpyProxy(object):
     """Stands in for the ``np`` global of a reference module: ``.random`` is the injected stream,
     everything else is the real numpy."""

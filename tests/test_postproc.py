@@ -3,6 +3,7 @@ CUDA kernels vs oracle (GPU)."""
 import numpy as np
 import pytest
 
+from oracle import postproc_oracle as po
 from oracle.postproc_oracle import StandardizeEnv, discount_cumsum, episode_stats_env, frame_stack_env, gae_env
 
 
@@ -91,6 +92,25 @@ def test_episode_stats_oracle_equals_reference_wrapper():
     assert len(got) == len(mine) >= 5
     for g, m in zip(got, mine):
         assert g[0] == m[0] and np.array_equal(g[1], m[1]) and g[2] == m[2] and g[3] == m[3] and g[4] == m[4]
+
+
+@pytest.mark.reference
+def test_batch_statistics_oracle_equals_rllab_functions():
+    """center_advantages / shift_advantages_to_positive / explained_variance_1d / discount_cumsum
+    of the oracle against the reference's own functions (rllab/rllab/algos/util.py:7-12,
+    rllab/rllab/misc/special.py:51-59,107-111), bit for bit."""
+    from oracle.refshim import load_rllab_numeric
+    util, special = load_rllab_numeric()
+    rs = np.random.RandomState(5)
+    for n in (1, 2, 17, 4096):
+        adv, y = rs.randn(n) * 3 + 1, rs.randn(n)
+        assert np.array_equal(po.center_advantages(adv), util.center_advantages(adv))
+        assert np.array_equal(po.shift_advantages_to_positive(adv), util.shift_advantages_to_positive(adv))
+        assert po.explained_variance_1d(adv, y) == special.explained_variance_1d(adv, y)
+        assert np.array_equal(discount_cumsum(adv, 0.97), special.discount_cumsum(adv, 0.97))
+    const = np.full(9, 2.5)
+    assert po.explained_variance_1d(const, const) == special.explained_variance_1d(const, const) == 1
+    assert po.explained_variance_1d(rs.randn(9), const) == special.explained_variance_1d(rs.randn(9), const) == 0
 
 
 def test_gae_oracle_matches_rllab_formulas():
@@ -182,3 +202,42 @@ def test_cuda_postproc_matches_oracle():
             assert np.abs(cat['episode_reward'][t, e] - ep_r).max() < 1e-4
             assert abs(cat['episode_avg_reward'][t, e] - avg) < 1e-4 and abs(cat['episode_disc_return'][t, e] - disc) < 1e-4
             assert cat['episode_length'][t, e] == length
+
+
+@pytest.mark.gpu
+def test_cuda_batch_statistics_match_oracle():
+    """madrl_center_advantages_f32 / madrl_moments_f32 against the oracle (float64 NumPy on the same
+    float32 inputs); tolerance 1e-5 relative to the value scale, results deterministic."""
+    import torch
+    from madrl_b200.postproc import center_advantages, explained_variance, moments
+    rs = np.random.RandomState(9)
+    for shape in ((1,), (3,), (50, 7, 3), (256, 4096, 5)):
+        adv = (rs.randn(*shape) * 3 + 1).astype(np.float32)
+        ret = rs.randn(*shape).astype(np.float32)
+        a_t, r_t = torch.as_tensor(adv, device='cuda'), torch.as_tensor(ret, device='cuda')
+        flat = adv.ravel().astype(np.float64)
+        for center, positive in ((True, False), (False, True), (True, True), (False, False)):
+            want = flat
+            if center:
+                want = po.center_advantages(want)
+            if positive:
+                want = po.shift_advantages_to_positive(want)
+            got = center_advantages(a_t, center=center, positive=positive)
+            assert got.shape == a_t.shape and got.data_ptr() != a_t.data_ptr()
+            tol = 1e-5 * max(1.0, np.abs(want).max())
+            assert np.abs(got.cpu().numpy().ravel() - want).max() <= tol
+            again = center_advantages(a_t, center=center, positive=positive)
+            assert torch.equal(got, again)                                 # deterministic reduction
+        assert torch.equal(a_t, torch.as_tensor(adv, device='cuda'))       # input untouched
+        st = moments(a_t, r_t).cpu().numpy()
+        r64 = ret.ravel().astype(np.float64)
+        want_st = np.array([flat.mean(), r64.mean(), (r64 - flat).mean(), flat.var(), r64.var(),
+                            (r64 - flat).var(), flat.min(), r64.min(), (r64 - flat).min()])
+        assert np.allclose(st, want_st, rtol=1e-10, atol=1e-12)
+        ev = explained_variance(a_t, r_t)
+        assert abs(ev - po.explained_variance_1d(flat, r64)) < 1e-9
+    const = torch.full((64,), 2.5, device='cuda')
+    assert explained_variance(const, const) == 1
+    assert explained_variance(torch.as_tensor(rs.randn(64).astype(np.float32), device='cuda'), const) == 0
+    out = center_advantages(const.clone(), inplace=True)                  # zero variance: 0 / 1e-8
+    assert torch.equal(out, torch.zeros_like(out))
