@@ -85,6 +85,40 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
 __device__ __forceinline__ void reds_add_u32(uint32_t a, uint32_t v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+// Staged sensing candidate in shared memory (one slot per object that survives the range cull):
+// {rx, ry, d2} = position relative to the sensing agent and its squared norm, {vx, vy} = velocity.
+// 32-bit shared addresses, vector accesses: one broadcast load per candidate in the sensor loops.
+template <typename real> struct CandSlot;
+template <> struct CandSlot<float> {
+  static constexpr uint32_t kStride = 32;   // +0 {rx, ry, d2, -}  +16 {vx, vy}
+  __device__ static __forceinline__ void put(uint32_t a, float rx, float ry, float d2, float vx, float vy) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %3};" ::"r"(a), "f"(rx), "f"(ry), "f"(d2) : "memory");
+    asm volatile("st.shared.v2.f32 [%0+16], {%1, %2};" ::"r"(a), "f"(vx), "f"(vy) : "memory");
+  }
+  __device__ static __forceinline__ void geom(uint32_t a, float& rx, float& ry, float& d2) {
+    float pad;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(rx), "=f"(ry), "=f"(d2), "=f"(pad) : "r"(a) : "memory");
+  }
+  __device__ static __forceinline__ void vel(uint32_t a, float& vx, float& vy) {
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+16];" : "=f"(vx), "=f"(vy) : "r"(a) : "memory");
+  }
+};
+template <> struct CandSlot<double> {
+  static constexpr uint32_t kStride = 48;   // +0 {rx, ry}  +16 {d2, -}  +32 {vx, vy}
+  __device__ static __forceinline__ void put(uint32_t a, double rx, double ry, double d2, double vx, double vy) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(rx), "d"(ry) : "memory");
+    asm volatile("st.shared.f64 [%0+16], %1;" ::"r"(a), "d"(d2) : "memory");
+    asm volatile("st.shared.v2.f64 [%0+32], {%1, %2};" ::"r"(a), "d"(vx), "d"(vy) : "memory");
+  }
+  __device__ static __forceinline__ void geom(uint32_t a, double& rx, double& ry, double& d2) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rx), "=d"(ry) : "r"(a) : "memory");
+    asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(d2) : "r"(a) : "memory");
+  }
+  __device__ static __forceinline__ void vel(uint32_t a, double& vx, double& vy) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+32];" : "=d"(vx), "=d"(vy) : "r"(a) : "memory");
+  }
+};
+
 // Pull a line towards L1/L2 without occupying a register (next step's action).
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 

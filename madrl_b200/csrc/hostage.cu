@@ -61,6 +61,11 @@ __device__ __forceinline__ real unit_at(uint64_t seed, uint32_t env_id, uint64_t
   return (real)(stream_word(seed, env_id, 0u, n) >> 8) * (real)(1.0 / 16777216.0);
 }
 
+#ifndef MADRL_HW_DEFERRED_TAIL
+// 1: the observation tail of every rescuer is written once per step from the any-collision masks
+// the reward logic computes anyway, instead of a ballot + a 6-lane store per rescuer.
+#define MADRL_HW_DEFERRED_TAIL 1
+#endif
 template <typename real, int OPL, int KCH, int KC>
 __global__ void __launch_bounds__(128, (OPL <= 2 ? 7 : 4))
 hw_kernel(const __grid_constant__ HWParams<real> p) {
@@ -90,7 +95,9 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
     sx_l[kc] = (k < K) ? p.sensors[k] : (real)0;
     sy_l[kc] = (k < K) ? p.sensors[K + k] : (real)0;
   }
+#if !MADRL_HW_DEFERRED_TAIL
   const int n_tail = 5 + (p.addid ? 1 : 0);
+#endif
   typedef typename HVec2<real>::type V2;
 
   for (int e = warp_global; e < p.E; e += warp_stride) {
@@ -238,7 +245,9 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
               bB[kc] = ok ? sv : INF;
             }
           }
+#if !MADRL_HW_DEFERRED_TAIL
           unsigned hitC = 0u, hitH = 0u;
+#endif
 #pragma unroll
           for (int c = 0; c < OPL; ++c) {
             const real rx = x[c] - mx, ry = y[c] - my;
@@ -246,10 +255,12 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
             // saved hostages are invisible (pre-step mask, hw:301) but still collide (hw:269-275)
             const unsigned cm = __ballot_sync(FULL_MASK, d2 <= cull2_l[c] && !sav[c]);
             const bool hit = d2 <= coll2_l[c];
-            const unsigned hb = __ballot_sync(FULL_MASK, hit);
             if (hit) col[c] |= 1u << pi;
+#if !MADRL_HW_DEFERRED_TAIL
+            const unsigned hb = __ballot_sync(FULL_MASK, hit);
             hitC |= hb & mC[c];
             hitH |= hb & mH[c];
+#endif
 #pragma unroll
             for (int kc = 0; kc < KCH; ++kc) {
               const real sx = sx_l[kc], sy = sy_l[kc];
@@ -300,6 +311,7 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
               store_stream(o + 4 * K, bB[kc] < INF ? bB[kc] : z);
             }
           }
+#if !MADRL_HW_DEFERRED_TAIL
           // tail hw:406-421: coll_ho, coll_cr, coll_key, coll_bomb, gate_open (post), id -- one
           // branch-free store
           if (lane < n_tail) {
@@ -308,6 +320,7 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
             const real tv = lane < 5 ? (real)((bits >> lane) & 1u) : (real)(pi + 1);
             store_stream(obs_row + 5 * K, tv);
           }
+#endif
         }
         // ---- process collisions + rewards: hw:274-284, 368-392 ---------------------------------------
         unsigned whoH = 0u, whoEnc = 0u, whoC = 0u;
@@ -341,6 +354,19 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
         whoH = __reduce_or_sync(FULL_MASK, whoH);
         whoEnc = __reduce_or_sync(FULL_MASK, whoEnc);
         whoC = __reduce_or_sync(FULL_MASK, whoC);
+#if MADRL_HW_DEFERRED_TAIL
+        // tail hw:406-421 of every rescuer's row: coll_ho, coll_cr, coll_key, coll_bomb, gate_open
+        // (post), id; lane i writes rescuer i's.  whoEnc / whoC are exactly the any-collision masks.
+        if (lane < p.Nr) {
+          real* tp = obs_t + (size_t)lane * p.D + 5 * K;
+          store_stream(tp, (real)((whoEnc >> lane) & 1u));
+          store_stream(tp + 1, (real)((whoC >> lane) & 1u));
+          store_stream(tp + 2, (real)((coll_ke >> lane) & 1u));
+          store_stream(tp + 3, (real)((coll_bo >> lane) & 1u));
+          store_stream(tp + 4, gate_post ? (real)1 : (real)0);
+          if (p.addid) store_stream(tp + 5, (real)(lane + 1));
+        }
+#endif
         if (coll_bo) flags |= 2;
         if (coll_ke) flags |= 1;
         const bool bombed = flags & 2;

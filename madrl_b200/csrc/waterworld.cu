@@ -37,6 +37,7 @@ struct WWParams {
   // per-step pointer bumps are plain 64-bit adds on constant-bank operands)
   size_t obs_step, agent_step;   // E*Np*D and E*Np
   real r_p2, range, cull2;                           // sensing thresholds (ww:68-69)
+  real range_up;                                     // nextafter(range, +inf): `sv < range_up` <=> `sv <= range`
   real coll2_e, coll2_po;                            // (r_p + r_obj) as exact squared thresholds
   real obst2_p, obst2_e, obst2_po;                   // (r_class + R_obst)       ww:251,259,267
   real resp2_p, resp2_e, resp2_po;                   // (2 r_class + R_obst)     ww:140
@@ -117,6 +118,28 @@ __device__ __noinline__ Spawn<real> spawn_object(uint64_t seed, uint32_t env_id,
 #ifndef MADRL_WW_MERGED_SCAN
 #define MADRL_WW_MERGED_SCAN 0   // 1: single candidate loop with a uniform class branch (experiment)
 #endif
+#ifndef MADRL_WW_DEFERRED_TAIL
+// 1: the per-pursuer "touched an evader / a poison" observation tail (ww:411-428) is written once
+// per step from the pursuer masks the catch logic computes anyway (a pursuer touched an evader iff
+// it is in the encounter set, ww:376; a poison iff it is in the poison-catch set, ww:293) instead of
+// one extra ballot + a 3-lane store per pursuer inside the sensing loop.
+#define MADRL_WW_DEFERRED_TAIL 1
+#endif
+#ifndef MADRL_WW_SMEM_MIN_OPL
+// Kernels with at least this many objects per lane stage the objects that survive the range cull
+// in per-warp shared memory slots (ascending object order): the sensor lanes then walk the slots
+// with one broadcast vector load per candidate instead of three shuffles + find-first-set
+// bookkeeping, and fetch the winner's velocity with one load instead of per-chunk shuffles.  Same
+// arithmetic, same candidate order => bit-identical results.  It costs ~25 instructions per pursuer
+// up front and saves ~9 per candidate, so it only pays when a pursuer sees many objects (C4-like
+// configurations); 99 = never.
+#define MADRL_WW_SMEM_MIN_OPL 99
+#endif
+#ifndef MADRL_WW_SMEM_UNROLL
+#define MADRL_WW_SMEM_UNROLL 2     // candidates per slot-loop iteration
+#endif
+#define MADRL_PRAGMA_(x) _Pragma(#x)
+#define MADRL_PRAGMA(x) MADRL_PRAGMA_(x)
 #ifndef MADRL_WW_MINBLOCKS_OPL4
 #define MADRL_WW_MINBLOCKS_OPL4 7   // resident 128-thread blocks per SM requested for 65..128 objects
 #endif
@@ -132,6 +155,10 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
   const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int warp_stride = gridDim.x * warps_per_block;
   const int eLo = p.Np, eHi = p.Np + p.Ne, Nall = p.Nall;
+  constexpr bool SMEM = OPL >= MADRL_WW_SMEM_MIN_OPL;
+  extern __shared__ __align__(16) unsigned char ww_smem[];
+  // this warp's candidate slots (32-bit shared address)
+  const uint32_t slots = SMEM ? smem_addr(ww_smem) + (threadIdx.x >> 5) * (uint32_t)Nall * CandSlot<real>::kStride : 0u;
 
   // ---- per-lane constants: this lane as OBJECT (classes, thresholds) and as SENSOR -----------
   real cull2_l[OPL], coll2_l[OPL];
@@ -154,7 +181,9 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     sy_l[kc] = (k < K) ? p.sensors[K + k] : (real)0;
   }
   const int n_feat = p.speed_features ? 7 : 4;
+#if !MADRL_WW_DEFERRED_TAIL
   const int n_tail = 2 + (p.addid ? 1 : 0);
+#endif
   typedef typename Vec2<real>::type V2;
 
   for (int e = warp_global; e < p.E; e += warp_stride) {
@@ -273,7 +302,87 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
               bO[kc] = ok ? sv : INF;
             }
           }
+#if !MADRL_WW_DEFERRED_TAIL
           unsigned hitE = 0u, hitP = 0u;
+#endif
+          if constexpr (SMEM) {
+            constexpr uint32_t S = CandSlot<real>::kStride;
+            uint32_t endU = slots, nEc = 0u, nPc = 0u, top = slots;
+#pragma unroll
+            for (int c = 0; c < OPL; ++c) {
+              // lanes as OBJECTS: geometry, collisions (ww:278-293), conservative range cull, staging
+              const real rx = x[c] - mx, ry = y[c] - my;
+              const real d2 = rx * rx + ry * ry;
+              const bool near = d2 <= cull2_l[c] && !(c == 0 && lane == pi);   // ww:70-71 `same`
+              const unsigned cm = __ballot_sync(FULL_MASK, near);
+              const bool hit = d2 <= coll2_l[c];
+              if (hit) col[c] |= 1u << pi;
+#if !MADRL_WW_DEFERRED_TAIL
+              const unsigned hb = __ballot_sync(FULL_MASK, hit);
+              hitE |= hb & mE[c];
+              hitP |= hb & mP[c];
+#endif
+              // slot = rank among the candidates in ascending object index (= lane + 32 c)
+              if (near) CandSlot<real>::put(top + (uint32_t)__popc(cm & ((1u << lane) - 1u)) * S, rx, ry, d2, vx[c], vy[c]);
+              if (c == 0) endU = slots + (uint32_t)__popc(cm & mU[0]) * S;   // pursuers live in chunk 0 (Np <= 32)
+              nEc += (uint32_t)__popc(cm & mE[c]);
+              nPc += (uint32_t)__popc(cm & mP[c]);
+              top += (uint32_t)__popc(cm) * S;
+            }
+            __syncwarp();
+            // lanes as SENSORS: classes are contiguous in object index, hence in slot order U, E, P
+            const uint32_t endE = endU + nEc * S, endP = endE + nPc * S;
+            const real up = p.range_up;   // `sv < up` <=> `sv <= range`; a best below `up` <=> sensed
+            uint32_t aE[KCH], aP[KCH], aU[KCH];
+#pragma unroll
+            for (int kc = 0; kc < KCH; ++kc) { bE[kc] = bP[kc] = bU[kc] = up; aE[kc] = aP[kc] = aU[kc] = slots; }
+#define MADRL_WW_SCAN(A0, A1, BEST, AT)                                                  \
+  MADRL_PRAGMA(unroll MADRL_WW_SMEM_UNROLL)                                              \
+  for (uint32_t a = (A0); a != (A1); a += S) {                                           \
+    real jx, jy, jd;                                                                     \
+    CandSlot<real>::geom(a, jx, jy, jd);                                                 \
+    _Pragma("unroll") for (int kc = 0; kc < KCH; ++kc) {                                 \
+      const real sv = sx_l[kc] * jx + sy_l[kc] * jy;                                     \
+      const bool ok = !((sv < (real)0) | (jd - sv * sv > p.r_p2));                       \
+      if (ok && sv < BEST[kc]) { BEST[kc] = sv; AT[kc] = a; }                            \
+    }                                                                                    \
+  }
+            MADRL_WW_SCAN(slots, endU, bU, aU)
+            MADRL_WW_SCAN(endU, endE, bE, aE)
+            MADRL_WW_SCAN(endE, endP, bP, aP)
+#undef MADRL_WW_SCAN
+#pragma unroll
+            for (int kc = 0; kc < KCH; ++kc) {
+              const real sx = sx_l[kc], sy = sy_l[kc];
+              // features ww:312-353, 388-395: feature-major, sensor-minor
+              const int k = lane + 32 * kc;
+              const bool hO = bO[kc] < INF, hE = bE[kc] < up, hP = bP[kc] < up, hU = bU[kc] < up;
+              const real z = (real)0;
+              real* o = obs_row + 32 * kc;   // this lane's column
+              if (p.speed_features) {
+                // slot 0 is read when nothing was sensed; its (possibly stale) value is masked below
+                real oEx, oEy, oPx, oPy, oUx, oUy;
+                CandSlot<real>::vel(aE[kc], oEx, oEy);
+                CandSlot<real>::vel(aP[kc], oPx, oPy);
+                CandSlot<real>::vel(aU[kc], oUx, oUy);
+                if (k < K) {
+                  store_stream(o + 0 * K, hO ? bO[kc] : z);
+                  store_stream(o + 1 * K, hE ? bE[kc] : z);
+                  store_stream(o + 2 * K, hE ? sx * (oEx - mvx) + sy * (oEy - mvy) : z);
+                  store_stream(o + 3 * K, hP ? bP[kc] : z);
+                  store_stream(o + 4 * K, hP ? sx * (oPx - mvx) + sy * (oPy - mvy) : z);
+                  store_stream(o + 5 * K, hU ? bU[kc] : z);
+                  store_stream(o + 6 * K, hU ? sx * (oUx - mvx) + sy * (oUy - mvy) : z);
+                }
+              } else if (k < K) {
+                store_stream(o + 0 * K, hO ? bO[kc] : z);
+                store_stream(o + 1 * K, hE ? bE[kc] : z);
+                store_stream(o + 2 * K, hP ? bP[kc] : z);
+                store_stream(o + 3 * K, hU ? bU[kc] : z);
+              }
+            }
+            __syncwarp();   // the next pursuer's staging overwrites the slots
+          } else {
 #pragma unroll
           for (int c = 0; c < OPL; ++c) {
             // lanes as OBJECTS: geometry, collisions (ww:278-293), conservative range cull
@@ -282,10 +391,12 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
             unsigned cm = __ballot_sync(FULL_MASK, d2 <= cull2_l[c]);
             if (c == 0) cm &= ~(1u << pi);  // ww:70-71 `same`
             const bool hit = d2 <= coll2_l[c];
-            const unsigned hb = __ballot_sync(FULL_MASK, hit);
             if (hit) col[c] |= 1u << pi;
+#if !MADRL_WW_DEFERRED_TAIL
+            const unsigned hb = __ballot_sync(FULL_MASK, hit);
             hitE |= hb & mE[c];
             hitP |= hb & mP[c];
+#endif
             // lanes as SENSORS: scan the surviving candidates of this chunk, ascending index
 #if MADRL_WW_MERGED_SCAN
             // one loop over all candidates; the class of candidate j is warp-uniform
@@ -370,12 +481,15 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
               store_stream(o + 3 * K, hU ? bU[kc] : z);
             }
           }
+          }
+#if !MADRL_WW_DEFERRED_TAIL
           // ww:411-428 tail: collided-with-evader, collided-with-poison, id -- one branch-free store
           if (lane < n_tail) {
             const unsigned bits = (hitE ? 1u : 0u) | (hitP ? 2u : 0u);
             const real tv = lane < 2 ? (real)((bits >> lane) & 1u) : (real)(pi + 1);
             store_stream(obs_row + n_feat * K, tv);
           }
+#endif
         }
         // ---- catches, respawn, rewards: ww:285,293,358-385 -----------------------------------------
         unsigned whoE = 0u, whoP = 0u, whoEnc = 0u;
@@ -406,6 +520,16 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
         whoE = __reduce_or_sync(FULL_MASK, whoE);
         whoP = __reduce_or_sync(FULL_MASK, whoP);
         whoEnc = __reduce_or_sync(FULL_MASK, whoEnc);
+#if MADRL_WW_DEFERRED_TAIL
+        // ww:411-428 tail of every pursuer's row: [touched an evader, touched a poison, id]; lane i
+        // writes pursuer i's.  whoEnc / whoP are exactly the any-collision masks (ww:376, ww:293).
+        if (lane < p.Np) {
+          real* tp = obs_t + (size_t)lane * p.D + n_feat * K;
+          store_stream(tp, (real)((whoEnc >> lane) & 1u));
+          store_stream(tp + 1, (real)((whoP >> lane) & 1u));
+          if (p.addid) store_stream(tp + 2, (real)(lane + 1));
+        }
+#endif
         if (!pass && lane < p.Np) {
           real r = pen;
           if (p.reward_global) {
@@ -658,12 +782,16 @@ template <typename real, int OPL, int KCH, int KC, bool PEER>
 static int ww_launch_inst2(madrl_ww* h, const WWParams<real>& p, cudaStream_t stream) {
   const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 4;
   int resident = 0;
-  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ww_kernel<real, OPL, KCH, KC, PEER>, wpb * 32, 0));
+  const size_t smem = OPL >= MADRL_WW_SMEM_MIN_OPL ? (size_t)wpb * p.Nall * CandSlot<real>::kStride : 0;
+  if (smem > 48 * 1024)
+    MADRL_CUDA_CHECK(cudaFuncSetAttribute(ww_kernel<real, OPL, KCH, KC, PEER>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ww_kernel<real, OPL, KCH, KC, PEER>, wpb * 32, smem));
   if (resident < 1) resident = 1;
   if (h->blocks_per_sm > 0 && h->blocks_per_sm < resident) resident = h->blocks_per_sm;
   int grid = (p.E + wpb - 1) / wpb;                  // one warp per env ...
   if (grid > h->sms * resident) grid = h->sms * resident;  // ... or a single persistent wave
-  ww_kernel<real, OPL, KCH, KC, PEER><<<grid, wpb * 32, 0, stream>>>(p);
+  ww_kernel<real, OPL, KCH, KC, PEER><<<grid, wpb * 32, smem, stream>>>(p);
   g_launches.fetch_add(1);
   MADRL_CUDA_CHECK(cudaGetLastError());
   return MADRL_OK;
@@ -693,6 +821,7 @@ static int ww_launch(madrl_ww* h, int mode, int T, const void* actions, void* ob
   const double r_p = c.radius, r_e = c.radius * 2, r_po = c.radius * 3 / 4;
   p.r_p2 = (real)(r_p * r_p);
   p.range = (real)c.sensor_range;
+  p.range_up = std::nextafter(p.range, (real)INFINITY);
   // Exact conservative cull: sv <= range and d2 - sv^2 <= r^2 imply d2 <= range^2 + r^2.
   p.cull2 = (real)((c.sensor_range * c.sensor_range + r_p * r_p) * (1.0 + 1e-4) + 1e-12);
   p.coll2_e = exact_sq_threshold<real>(r_p + r_e);
