@@ -64,7 +64,7 @@ __device__ __forceinline__ real unit_at(uint64_t seed, uint32_t env_id, uint64_t
 #ifndef MADRL_HW_DEFERRED_TAIL
 // 1: the observation tail of every rescuer is written once per step from the any-collision masks
 // the reward logic computes anyway, instead of a ballot + a 6-lane store per rescuer.
-#define MADRL_HW_DEFERRED_TAIL 1
+#define MADRL_HW_DEFERRED_TAIL 0
 #endif
 template <typename real, int OPL, int KCH, int KC>
 __global__ void __launch_bounds__(128, (OPL <= 2 ? 7 : 4))
@@ -358,7 +358,7 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
         // tail hw:406-421 of every rescuer's row: coll_ho, coll_cr, coll_key, coll_bomb, gate_open
         // (post), id; lane i writes rescuer i's.  whoEnc / whoC are exactly the any-collision masks.
         if (lane < p.Nr) {
-          real* tp = obs_t + (size_t)lane * p.D + 5 * K;
+          real* tp = obs_t + (size_t)lane * (p.D - 1) + 5 * K;   // obs_t already carries +lane
           store_stream(tp, (real)((whoEnc >> lane) & 1u));
           store_stream(tp + 1, (real)((whoC >> lane) & 1u));
           store_stream(tp + 2, (real)((coll_ke >> lane) & 1u));

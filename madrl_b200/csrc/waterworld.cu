@@ -123,7 +123,7 @@ __device__ __noinline__ Spawn<real> spawn_object(uint64_t seed, uint32_t env_id,
 // per step from the pursuer masks the catch logic computes anyway (a pursuer touched an evader iff
 // it is in the encounter set, ww:376; a poison iff it is in the poison-catch set, ww:293) instead of
 // one extra ballot + a 3-lane store per pursuer inside the sensing loop.
-#define MADRL_WW_DEFERRED_TAIL 1
+#define MADRL_WW_DEFERRED_TAIL 0
 #endif
 #ifndef MADRL_WW_SMEM_MIN_OPL
 // Kernels with at least this many objects per lane stage the objects that survive the range cull
@@ -524,7 +524,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
         // ww:411-428 tail of every pursuer's row: [touched an evader, touched a poison, id]; lane i
         // writes pursuer i's.  whoEnc / whoP are exactly the any-collision masks (ww:376, ww:293).
         if (lane < p.Np) {
-          real* tp = obs_t + (size_t)lane * p.D + n_feat * K;
+          real* tp = obs_t + (size_t)lane * (p.D - 1) + n_feat * K;   // obs_t already carries +lane
           store_stream(tp, (real)((whoEnc >> lane) & 1u));
           store_stream(tp + 1, (real)((whoP >> lane) & 1u));
           if (p.addid) store_stream(tp + 2, (real)(lane + 1));
