@@ -64,7 +64,7 @@ __device__ __forceinline__ real unit_at(uint64_t seed, uint32_t env_id, uint64_t
 #ifndef MADRL_HW_DEFERRED_TAIL
 // 1: the observation tail of every rescuer is written once per step from the any-collision masks
 // the reward logic computes anyway, instead of a ballot + a 6-lane store per rescuer.
-#define MADRL_HW_DEFERRED_TAIL 0
+#define MADRL_HW_DEFERRED_TAIL 1
 #endif
 template <typename real, int OPL, int KCH, int KC>
 __global__ void __launch_bounds__(128, (OPL <= 2 ? 7 : 4))

@@ -123,7 +123,7 @@ __device__ __noinline__ Spawn<real> spawn_object(uint64_t seed, uint32_t env_id,
 // per step from the pursuer masks the catch logic computes anyway (a pursuer touched an evader iff
 // it is in the encounter set, ww:376; a poison iff it is in the poison-catch set, ww:293) instead of
 // one extra ballot + a 3-lane store per pursuer inside the sensing loop.
-#define MADRL_WW_DEFERRED_TAIL 0
+#define MADRL_WW_DEFERRED_TAIL 1
 #endif
 #ifndef MADRL_WW_SMEM_MIN_OPL
 // Kernels with at least this many objects per lane stage the objects that survive the range cull
