@@ -85,6 +85,14 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
 __device__ __forceinline__ void reds_add_u32(uint32_t a, uint32_t v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+// Experiment: launch the warp-per-env kernels as 32-thread blocks.  The env index then derives from
+// blockIdx alone, so ptxas can prove the persistent loop and every branch on warp-uniform values
+// uniform: the BRA.DIV guards in front of the warp collectives disappear, loop bookkeeping moves to
+// the uniform datapath and the register count drops (Waterworld C2: 72 regs + spills -> 56, none).
+#ifndef MADRL_ONE_WARP_BLOCKS
+#define MADRL_ONE_WARP_BLOCKS 0
+#endif
+
 // Staged sensing candidate in shared memory (one slot per object that survives the range cull):
 // {rx, ry, d2} = position relative to the sensing agent and its squared norm, {vx, vy} = velocity.
 // 32-bit shared addresses, vector accesses: one broadcast load per candidate in the sensor loops.
@@ -96,8 +104,7 @@ template <> struct CandSlot<float> {
     asm volatile("st.shared.v2.f32 [%0+16], {%1, %2};" ::"r"(a), "f"(vx), "f"(vy) : "memory");
   }
   __device__ static __forceinline__ void geom(uint32_t a, float& rx, float& ry, float& d2) {
-    float pad;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(rx), "=f"(ry), "=f"(d2), "=f"(pad) : "r"(a) : "memory");
+    asm volatile("{ .reg .f32 pad; ld.shared.v4.f32 {%0, %1, %2, pad}, [%3]; }" : "=f"(rx), "=f"(ry), "=f"(d2) : "r"(a) : "memory");
   }
   __device__ static __forceinline__ void vel(uint32_t a, float& vx, float& vy) {
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+16];" : "=f"(vx), "=f"(vy) : "r"(a) : "memory");

@@ -66,15 +66,28 @@ __device__ __forceinline__ real unit_at(uint64_t seed, uint32_t env_id, uint64_t
 // the reward logic computes anyway, instead of a ballot + a 6-lane store per rescuer.
 #define MADRL_HW_DEFERRED_TAIL 1
 #endif
+#ifndef MADRL_HW_ONE_WARP_BLOCKS
+#define MADRL_HW_ONE_WARP_BLOCKS MADRL_ONE_WARP_BLOCKS   // see common.cuh
+#endif
 template <typename real, int OPL, int KCH, int KC>
+#if MADRL_HW_ONE_WARP_BLOCKS
+__global__ void __launch_bounds__(32, (OPL <= 2 ? 28 : 16))
+#else
 __global__ void __launch_bounds__(128, (OPL <= 2 ? 7 : 4))
+#endif
 hw_kernel(const __grid_constant__ HWParams<real> p) {
   const real INF = real_inf<real>();
   const int K = KC > 0 ? KC : p.K;
+#if MADRL_HW_ONE_WARP_BLOCKS
+  const int lane = threadIdx.x;
+  const int warp_global = blockIdx.x;
+  const int warp_stride = gridDim.x;
+#else
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int warp_stride = gridDim.x * warps_per_block;
+#endif
   const int cLo = p.Nr, hLo = p.Nr + p.Nc, Nall = p.Nall;
 
   real cull2_l[OPL], coll2_l[OPL];
@@ -562,7 +575,11 @@ static real hw_exact_sq_threshold(double thr_d) {
 
 template <typename real, int OPL, int KCH, int KC>
 static int hw_launch_inst(madrl_hostage* h, const HWParams<real>& p, cudaStream_t stream) {
+#if MADRL_HW_ONE_WARP_BLOCKS
+  const int wpb = 1;
+#else
   const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 4;
+#endif
   int resident = 0;
   MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, hw_kernel<real, OPL, KCH, KC>, wpb * 32, 0));
   if (resident < 1) resident = 1;

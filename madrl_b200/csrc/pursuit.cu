@@ -88,13 +88,24 @@ __device__ __forceinline__ double numpy_mean(const double* a, int n) {
 #ifndef MADRL_PE_MINBLOCKS
 #define MADRL_PE_MINBLOCKS 7   // resident 128-thread blocks per SM requested (7 -> 72 registers)
 #endif
+#ifndef MADRL_PE_ONE_WARP_BLOCKS
+#define MADRL_PE_ONE_WARP_BLOCKS MADRL_ONE_WARP_BLOCKS   // see common.cuh
+#endif
 template <int EPL, int CPL, int RC>
+#if MADRL_PE_ONE_WARP_BLOCKS
+__global__ void __launch_bounds__(32, 4 * MADRL_PE_MINBLOCKS) pe_kernel(const __grid_constant__ PEParams p) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  const int lane = threadIdx.x, wib = 0;
+  const int warp_global = blockIdx.x;
+  const int warp_stride = gridDim.x;
+#else
 __global__ void __launch_bounds__(128, MADRL_PE_MINBLOCKS) pe_kernel(const __grid_constant__ PEParams p) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
   const int warp_global = blockIdx.x * warps_per_block + wib;
   const int warp_stride = gridDim.x * warps_per_block;
+#endif
   const int R = RC > 0 ? RC : p.R, RR = R * R, xs = p.xs, ys = p.ys, ncell = xs * ys;
   const int Np = p.Np, Ne = p.Ne, Nag = Np + Ne;
 
@@ -530,7 +541,11 @@ extern "C" int madrl_pursuit_set_params(madrl_pursuit* h, double catchr, double 
 
 template <int EPL, int CPL, int RC>
 static int pe_launch_inst(madrl_pursuit* h, PEParams& p, cudaStream_t stream) {
+#if MADRL_PE_ONE_WARP_BLOCKS
+  const int wpb = 1;
+#else
   const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 4;
+#endif
   const size_t smem = 1024 + (size_t)wpb * p.smem_per_warp;   // block LUT + per-warp regions
   MADRL_REQUIRE(smem <= 200 * 1024, "map too large for shared memory (%zu B per block)", smem);
   if (smem > 48 * 1024)

@@ -125,6 +125,9 @@ __device__ __noinline__ Spawn<real> spawn_object(uint64_t seed, uint32_t env_id,
 // one extra ballot + a 3-lane store per pursuer inside the sensing loop.
 #define MADRL_WW_DEFERRED_TAIL 1
 #endif
+#ifndef MADRL_WW_ONE_WARP_BLOCKS
+#define MADRL_WW_ONE_WARP_BLOCKS MADRL_ONE_WARP_BLOCKS   // see common.cuh
+#endif
 #ifndef MADRL_WW_SMEM_MIN_OPL
 // Kernels with at least this many objects per lane stage the objects that survive the range cull
 // in per-warp shared memory slots (ascending object order): the sensor lanes then walk the slots
@@ -146,19 +149,32 @@ __device__ __noinline__ Spawn<real> spawn_object(uint64_t seed, uint32_t env_id,
 // PEER = compile the fused multi-GPU exchange in (a separate instantiation, so the single-GPU kernel
 // carries none of its registers).
 template <typename real, int OPL, int KCH, int KC, bool PEER>
+#if MADRL_WW_ONE_WARP_BLOCKS
+__global__ void __launch_bounds__(32, (OPL <= 2 ? 28 : (OPL <= 4 ? 4 * MADRL_WW_MINBLOCKS_OPL4 : 16)))
+#else
 __global__ void __launch_bounds__(128, (OPL <= 2 ? 7 : (OPL <= 4 ? MADRL_WW_MINBLOCKS_OPL4 : 4)))
+#endif
 ww_kernel(const __grid_constant__ WWParams<real> p) {
   const real INF = real_inf<real>();
   const int K = KC > 0 ? KC : p.K;
+#if MADRL_WW_ONE_WARP_BLOCKS
+  // 32-thread blocks: the env index derives from blockIdx alone, so the compiler can prove every
+  // loop and branch on it warp-uniform (experiment: drops the BRA.DIV guards in front of the warp
+  // collectives and moves loop bookkeeping to the uniform datapath).
+  const int lane = threadIdx.x;
+  const int warp_global = blockIdx.x;
+  const int warp_stride = gridDim.x;
+#else
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int warp_stride = gridDim.x * warps_per_block;
+#endif
   const int eLo = p.Np, eHi = p.Np + p.Ne, Nall = p.Nall;
   constexpr bool SMEM = OPL >= MADRL_WW_SMEM_MIN_OPL;
   extern __shared__ __align__(16) unsigned char ww_smem[];
   // this warp's candidate slots (32-bit shared address)
-  const uint32_t slots = SMEM ? smem_addr(ww_smem) + (threadIdx.x >> 5) * (uint32_t)Nall * CandSlot<real>::kStride : 0u;
+  const uint32_t slots = SMEM ? smem_addr(ww_smem) + (MADRL_WW_ONE_WARP_BLOCKS ? 0u : (threadIdx.x >> 5)) * (uint32_t)Nall * CandSlot<real>::kStride : 0u;
 
   // ---- per-lane constants: this lane as OBJECT (classes, thresholds) and as SENSOR -----------
   real cull2_l[OPL], coll2_l[OPL];
@@ -780,7 +796,11 @@ static real exact_sq_threshold(double thr_d) {
 
 template <typename real, int OPL, int KCH, int KC, bool PEER>
 static int ww_launch_inst2(madrl_ww* h, const WWParams<real>& p, cudaStream_t stream) {
+#if MADRL_WW_ONE_WARP_BLOCKS
+  const int wpb = 1;
+#else
   const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 4;
+#endif
   int resident = 0;
   const size_t smem = OPL >= MADRL_WW_SMEM_MIN_OPL ? (size_t)wpb * p.Nall * CandSlot<real>::kStride : 0;
   if (smem > 48 * 1024)
