@@ -57,9 +57,31 @@ __device__ __forceinline__ void store_stream(T* p, T v) {
 #endif
 }
 
+// Experiment: launch the warp-per-env kernels as 32-thread blocks.  The env index then derives from
+// blockIdx alone, so ptxas can prove the persistent loop and every branch on warp-uniform values
+// uniform: the BRA.DIV guards in front of the warp collectives disappear, loop bookkeeping moves to
+// the uniform datapath and the register count drops (Waterworld C2: 72 regs + spills -> 56, none).
+#ifndef MADRL_ONE_WARP_BLOCKS
+#define MADRL_ONE_WARP_BLOCKS 0
+#endif
+
+// Kernels are launched through one macro and the PTX-level helpers below sit behind one guard so
+// that the test-only warp emulator (tests/emu: the kernels compiled by g++ against a fake
+// <cuda_runtime.h>, lanes run as fibers) can substitute host versions.  Neither is ever defined in
+// the product build.
+#ifndef MADRL_LAUNCH
+#define MADRL_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+#ifndef MADRL_EMU_PTX_HELPERS
 // Explicit shared-window accesses on 32-bit shared addresses.  Keeping ONE 32-bit base address
 // in a register (instead of a generic pointer the compiler re-derives from SR_CgaCtaId at every
 // use) removes 3-4 instructions per shared-memory access in the hot loops.
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
   uint32_t v;
@@ -85,14 +107,6 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
 __device__ __forceinline__ void reds_add_u32(uint32_t a, uint32_t v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
-// Experiment: launch the warp-per-env kernels as 32-thread blocks.  The env index then derives from
-// blockIdx alone, so ptxas can prove the persistent loop and every branch on warp-uniform values
-// uniform: the BRA.DIV guards in front of the warp collectives disappear, loop bookkeeping moves to
-// the uniform datapath and the register count drops (Waterworld C2: 72 regs + spills -> 56, none).
-#ifndef MADRL_ONE_WARP_BLOCKS
-#define MADRL_ONE_WARP_BLOCKS 0
-#endif
-
 // Staged sensing candidate in shared memory (one slot per object that survives the range cull):
 // {rx, ry, d2} = position relative to the sensing agent and its squared norm, {vx, vy} = velocity.
 // 32-bit shared addresses, vector accesses: one broadcast load per candidate in the sensor loops.
@@ -128,6 +142,7 @@ template <> struct CandSlot<double> {
 
 // Pull a line towards L1/L2 without occupying a register (next step's action).
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#endif  // MADRL_EMU_PTX_HELPERS
 
 template <typename real>
 __device__ __forceinline__ real clip01(real x) {

@@ -580,13 +580,14 @@ static int hw_launch_inst(madrl_hostage* h, const HWParams<real>& p, cudaStream_
 #else
   const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 4;
 #endif
+  const auto kfn = hw_kernel<real, OPL, KCH, KC>;
   int resident = 0;
-  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, hw_kernel<real, OPL, KCH, KC>, wpb * 32, 0));
+  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, wpb * 32, 0));
   if (resident < 1) resident = 1;
   if (h->blocks_per_sm > 0 && h->blocks_per_sm < resident) resident = h->blocks_per_sm;
   int grid = (p.E + wpb - 1) / wpb;
   if (grid > h->sms * resident) grid = h->sms * resident;
-  hw_kernel<real, OPL, KCH, KC><<<grid, wpb * 32, 0, stream>>>(p);
+  MADRL_LAUNCH(kfn, grid, wpb * 32, 0, stream, p);
   g_launches.fetch_add(1);
   MADRL_CUDA_CHECK(cudaGetLastError());
   return MADRL_OK;

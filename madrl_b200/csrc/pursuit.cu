@@ -55,12 +55,6 @@ struct PEParams {
   const uint8_t* mask;
 };
 
-__device__ __forceinline__ unsigned lanemask_lt() {
-  unsigned m;
-  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-  return m;
-}
-
 // float64 `ndarray.mean()` exactly as NumPy (>= 1.22, checked against 2.3.5) computes it for a
 // contiguous vector of n <= 128 elements: DOUBLE_pairwise_sum over the WHOLE vector
 // (numpy/_core/src/umath/loops_utils.h.src: n < 8 -> sequential from -0.0; else 8 interleaved
@@ -547,16 +541,17 @@ static int pe_launch_inst(madrl_pursuit* h, PEParams& p, cudaStream_t stream) {
   const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 4;
 #endif
   const size_t smem = 1024 + (size_t)wpb * p.smem_per_warp;   // block LUT + per-warp regions
+  const auto kfn = pe_kernel<EPL, CPL, RC>;
   MADRL_REQUIRE(smem <= 200 * 1024, "map too large for shared memory (%zu B per block)", smem);
   if (smem > 48 * 1024)
-    MADRL_CUDA_CHECK(cudaFuncSetAttribute(pe_kernel<EPL, CPL, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MADRL_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int resident = 0;
-  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pe_kernel<EPL, CPL, RC>, wpb * 32, smem));
+  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, wpb * 32, smem));
   if (resident < 1) resident = 1;
   if (h->blocks_per_sm > 0 && h->blocks_per_sm < resident) resident = h->blocks_per_sm;
   int grid = (p.E + wpb - 1) / wpb;
   if (grid > h->sms * resident) grid = h->sms * resident;
-  pe_kernel<EPL, CPL, RC><<<grid, wpb * 32, smem, stream>>>(p);
+  MADRL_LAUNCH(kfn, grid, wpb * 32, smem, stream, p);
   g_launches.fetch_add(1);
   MADRL_CUDA_CHECK(cudaGetLastError());
   return MADRL_OK;

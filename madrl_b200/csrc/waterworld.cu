@@ -801,17 +801,18 @@ static int ww_launch_inst2(madrl_ww* h, const WWParams<real>& p, cudaStream_t st
 #else
   const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 4;
 #endif
+  const auto kfn = ww_kernel<real, OPL, KCH, KC, PEER>;
   int resident = 0;
   const size_t smem = OPL >= MADRL_WW_SMEM_MIN_OPL ? (size_t)wpb * p.Nall * CandSlot<real>::kStride : 0;
   if (smem > 48 * 1024)
-    MADRL_CUDA_CHECK(cudaFuncSetAttribute(ww_kernel<real, OPL, KCH, KC, PEER>,
+    MADRL_CUDA_CHECK(cudaFuncSetAttribute(kfn,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ww_kernel<real, OPL, KCH, KC, PEER>, wpb * 32, smem));
+  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, wpb * 32, smem));
   if (resident < 1) resident = 1;
   if (h->blocks_per_sm > 0 && h->blocks_per_sm < resident) resident = h->blocks_per_sm;
   int grid = (p.E + wpb - 1) / wpb;                  // one warp per env ...
   if (grid > h->sms * resident) grid = h->sms * resident;  // ... or a single persistent wave
-  ww_kernel<real, OPL, KCH, KC, PEER><<<grid, wpb * 32, smem, stream>>>(p);
+  MADRL_LAUNCH(kfn, grid, wpb * 32, smem, stream, p);
   g_launches.fetch_add(1);
   MADRL_CUDA_CHECK(cudaGetLastError());
   return MADRL_OK;

@@ -1,0 +1,160 @@
+// TEST INFRASTRUCTURE -- fiber scheduler of the warp emulator (see include/cuda_runtime.h).
+//
+// One OS thread.  Every CUDA thread of the current block is a ucontext fiber; fibers run until they
+// reach a rendezvous (warp collective or block barrier), deposit their value and hand control back to
+// the scheduler, which resumes the next unfinished fiber round-robin.  A rendezvous completes when
+// all lanes of the warp (threads of the block) have arrived; lanes can be at most one rendezvous
+// apart, so two slot buffers indexed by the parity of the lane's rendezvous counter suffice.
+// Blocks of a grid run one after the other.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <ucontext.h>
+
+#include <vector>
+
+uint3 threadIdx, blockIdx;
+dim3 blockDim, gridDim;
+
+// The dynamic shared memory arrays the kernels declare with `extern __shared__` (block-scope extern
+// declarations inside namespace madrl resolve to these).
+namespace madrl {
+constexpr size_t kEmuSmemBytes = 256 * 1024;
+__attribute__((aligned(16))) unsigned char ww_smem[kEmuSmemBytes];
+__attribute__((aligned(16))) uint32_t smem_u32[kEmuSmemBytes / 4];
+}  // namespace madrl
+
+namespace madrl_emu {
+namespace {
+
+constexpr size_t kStackBytes = 256 * 1024;
+
+struct Rendezvous {          // per warp (collectives) or per block (barrier)
+  uint64_t slots[2][32];
+  long epoch[2] = {-1, -1};
+  int count[2] = {0, 0};
+};
+
+struct Fiber {
+  ucontext_t ctx;
+  char* stack = nullptr;
+  bool done = false;
+  long warp_phase = 0, block_phase = 0;
+  unsigned tid = 0;
+};
+
+std::vector<Fiber> g_fibers;
+std::vector<Rendezvous> g_warps;
+Rendezvous g_block;
+ucontext_t g_sched;
+int g_cur = -1;
+long g_progress = 0;          // bumped whenever a rendezvous completes or a fiber finishes
+const std::function<void()>* g_body = nullptr;
+
+void yield_to_scheduler() {
+  Fiber& f = g_fibers[g_cur];
+  swapcontext(&f.ctx, &g_sched);
+}
+
+void fiber_entry() {
+  (*g_body)();
+  g_fibers[g_cur].done = true;
+  ++g_progress;
+  yield_to_scheduler();
+  abort();   // a finished fiber is never resumed
+}
+
+}  // namespace
+
+unsigned char* smem_anchor() { return madrl::ww_smem; }
+
+void check_smem(size_t bytes) {
+  if (bytes > madrl::kEmuSmemBytes) {
+    fprintf(stderr, "madrl_emu: %zu bytes of dynamic shared memory requested, emulator has %zu\n", bytes,
+            madrl::kEmuSmemBytes);
+    abort();
+  }
+}
+
+const uint64_t* warp_exchange(uint64_t v) {
+  Fiber& f = g_fibers[g_cur];
+  Rendezvous& r = g_warps[f.tid >> 5];
+  const long ph = f.warp_phase++;
+  const int p = (int)(ph & 1);
+  if (r.epoch[p] != ph) { r.epoch[p] = ph; r.count[p] = 0; }
+  r.slots[p][f.tid & 31] = v;
+  if (++r.count[p] == 32) ++g_progress;
+  while (r.count[p] < 32 || r.epoch[p] != ph) yield_to_scheduler();
+  return r.slots[p];
+}
+
+void block_barrier() {
+  Fiber& f = g_fibers[g_cur];
+  const long ph = f.block_phase++;
+  const int p = (int)(ph & 1);
+  const int n = (int)g_fibers.size();
+  if (g_block.epoch[p] != ph) { g_block.epoch[p] = ph; g_block.count[p] = 0; }
+  if (++g_block.count[p] == n) ++g_progress;
+  while (g_block.count[p] < n || g_block.epoch[p] != ph) yield_to_scheduler();
+}
+
+void run_grid(unsigned grid, unsigned block, size_t smem, const std::function<void()>& body) {
+  if (block == 0 || block % 32 != 0) {
+    fprintf(stderr, "madrl_emu: block size %u is not a multiple of 32\n", block);
+    abort();
+  }
+  check_smem(smem);
+  g_body = &body;
+  gridDim = dim3(grid);
+  blockDim = dim3(block);
+  for (unsigned b = 0; b < grid; ++b) {
+    blockIdx = uint3{b, 0, 0};
+    // uninitialised shared memory must not be relied upon: poison it
+    memset(madrl::ww_smem, 0xCD, madrl::kEmuSmemBytes);
+    memset(madrl::smem_u32, 0xCD, madrl::kEmuSmemBytes);
+    g_fibers.assign(block, Fiber());
+    g_warps.assign(block / 32, Rendezvous());
+    g_block = Rendezvous();
+    for (unsigned t = 0; t < block; ++t) {
+      Fiber& f = g_fibers[t];
+      f.tid = t;
+      f.stack = static_cast<char*>(malloc(kStackBytes));
+      getcontext(&f.ctx);
+      f.ctx.uc_stack.ss_sp = f.stack;
+      f.ctx.uc_stack.ss_size = kStackBytes;
+      f.ctx.uc_link = nullptr;
+      makecontext(&f.ctx, fiber_entry, 0);
+    }
+    unsigned remaining = block;
+    long seen = g_progress;
+    unsigned idle_rounds = 0;
+    while (remaining > 0) {
+      unsigned ran = 0;
+      for (unsigned t = 0; t < block; ++t) {
+        Fiber& f = g_fibers[t];
+        if (f.done) continue;
+        g_cur = (int)t;
+        threadIdx = uint3{t, 0, 0};
+        swapcontext(&g_sched, &f.ctx);
+        ++ran;
+        if (f.done) --remaining;
+      }
+      if (g_progress == seen) {
+        // a full round in which no rendezvous completed and no fiber finished: some lanes wait for
+        // lanes that exited or took a different path -- a divergent collective, i.e. a kernel bug
+        if (++idle_rounds > 2) {
+          fprintf(stderr, "madrl_emu: deadlock in block %u (%u fibers waiting at a rendezvous the others never reach)\n", b, ran);
+          abort();
+        }
+      } else {
+        idle_rounds = 0;
+        seen = g_progress;
+      }
+    }
+    for (auto& f : g_fibers) free(f.stack);
+  }
+  g_fibers.clear();
+  g_cur = -1;
+  g_body = nullptr;
+}
+
+}  // namespace madrl_emu

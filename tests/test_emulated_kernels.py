@@ -1,0 +1,263 @@
+"""The KERNEL SOURCE (madrl_b200/csrc/*.cu) executed on the CPU by the warp emulator of tests/emu
+(g++ + a fake <cuda_runtime.h>; every CUDA thread is a fiber, warp collectives are rendezvous
+points) and compared with the oracle.  This is test infrastructure: it checks the C++ semantics of
+the kernels and of the host launch code without a GPU, for the default build and for the
+experiment flags that are still off in the product; the `-m gpu` tests remain the parity proof of
+what nvcc makes of the same source.  Nothing in madrl_b200/ can load the emulator library."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle.hostage_oracle import HostageOracle
+from oracle.philox import Stream
+from oracle.pursuit_oracle import PursuitOracle
+from oracle.waterworld_oracle import WaterworldOracle
+
+pytestmark = pytest.mark.skipif(shutil.which(os.environ.get("CXX", "g++")) is None, reason="no host C++ compiler")
+
+# build variants: the product defaults, and every experiment flag that is still off in the product
+VARIANTS = {
+    "default": (),
+    "experiments": ("-DMADRL_ONE_WARP_BLOCKS=1", "-DMADRL_WW_SMEM_MIN_OPL=1"),
+}
+
+
+def f32(x):
+    return np.asarray(x, dtype=np.float64).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------ Waterworld
+WW = {
+    "c2": dict(n_pursuers=5, n_evaders=5),
+    "dense": dict(n_pursuers=5, n_evaders=5, n_coop=1, radius=0.04, sensor_range=0.3),
+    "global_nospeed_randobst": dict(n_pursuers=3, n_evaders=4, n_poison=2, n_sensors=7, n_coop=1, radius=0.05,
+                                    reward_mech='global', speed_features=False, addid=False, obstacle_loc=None),
+    "c4": dict(n_pursuers=20, n_evaders=50, n_poison=50),                                     # 4 objects per lane
+    "k40": dict(n_pursuers=4, n_evaders=40, n_poison=3, n_sensors=40, n_coop=2, radius=0.03),  # 2 sensors per lane
+    "big200": dict(n_pursuers=6, n_evaders=120, n_poison=74, n_coop=2, radius=0.02),          # 8 objects per lane
+    "minimum": dict(n_pursuers=1, n_evaders=1, n_poison=1, n_sensors=1, n_coop=1, radius=0.05),
+    "np32_k64": dict(n_pursuers=32, n_evaders=3, n_poison=2, n_sensors=64, n_coop=3, radius=0.03),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("name,E,T", [("c2", 5, 60), ("dense", 5, 80), ("global_nospeed_randobst", 5, 80),
+                                      ("c4", 3, 8), ("k40", 3, 25), ("big200", 2, 6), ("minimum", 5, 60),
+                                      ("np32_k64", 2, 6)])
+def test_waterworld_fp64_trajectories_match_oracle(variant, name, E, T):
+    from emu.driver import EmuWaterworld
+    cfg = WW[name]
+    seed, base = 1234, 1000
+    eng = EmuWaterworld(E, seed=seed, env_id_base=base, defines=VARIANTS[variant], **cfg)
+    obs0 = eng.reset()
+    oracles = [WaterworldOracle(rng=Stream(seed, base + e), **cfg) for e in range(E)]
+    for e, o in enumerate(oracles):
+        assert np.abs(np.array(o.reset()) - obs0[e]).max() < 1e-9, e
+    Np = cfg['n_pursuers']
+    act = np.random.RandomState(5).randn(T, E, Np, 2) * 0.7
+    obs, rew, done, info = eng.rollout(act, auto_reset=False)
+    for t in range(T):
+        for e, o in enumerate(oracles):
+            oo, rr, dd, ii = o.step(act[t, e])
+            assert [ii['evcatches'], ii['pocatches']] == list(info[t, e]), (t, e)
+            assert np.abs(np.array(oo) - obs[t, e]).max() < 1e-9, (t, e)
+            assert np.abs(rr - rew[t, e]).max() < 1e-9, (t, e)
+            assert bool(done[t, e]) == dd
+    for e, o in enumerate(oracles):
+        s = eng.state(e)
+        assert s['counter'] == o.np_random.counter and s['t'] == o.t
+        assert np.abs(s['ex'] - o.ex).max() < 1e-9 and np.abs(s['pv'] - o.pv).max() < 1e-9
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_waterworld_auto_reset_horizon_mask_and_host_path(variant):
+    from emu.driver import EmuWaterworld
+    cfg = WW["c2"]
+    E, T, mpl, seed = 5, 20, 7, 4
+    eng = EmuWaterworld(E, seed=seed, max_path_length=mpl, defines=VARIANTS[variant], **cfg)
+    eng.reset()
+    act = np.random.RandomState(0).randn(T, E, 5, 2) * 0.5
+    obs, rew, done, info = eng.rollout(act, auto_reset=True)
+    oracles = [WaterworldOracle(rng=Stream(seed, e), **cfg) for e in range(E)]
+    for o in oracles:
+        o.reset()
+    ts = np.zeros(E, int)
+    for t in range(T):
+        for e, o in enumerate(oracles):
+            oo, rr, dd, ii = o.step(act[t, e])
+            ts[e] += 1
+            dd = dd or ts[e] >= mpl
+            assert bool(done[t, e]) == dd
+            if dd:
+                oo = o.reset()
+                ts[e] = 0
+            assert np.abs(np.array(oo) - obs[t, e]).max() < 1e-9, (t, e)
+            assert np.abs(rr - rew[t, e]).max() < 1e-9
+    assert done.sum() == E * (T // mpl)
+    # the host-buffer entry point gives the same trajectory as the device one
+    a, b = [EmuWaterworld(E, seed=9, defines=VARIANTS[variant], **cfg) for _ in range(2)]
+    a.reset(), b.reset()
+    for x, y in zip(a.rollout(act, host=False), b.rollout(act, host=True)):
+        assert np.array_equal(x, y)
+    # masked reset re-initialises only the selected envs
+    before = [a.state(e) for e in range(E)]
+    mask = np.array([1, 0, 0, 1, 0], np.uint8)
+    obs_r = a.reset(mask)
+    for e in range(E):
+        s = a.state(e)
+        if mask[e]:
+            assert s['t'] == 1 and np.abs(obs_r[e]).sum() > 0
+        else:
+            assert s['t'] == before[e]['t'] and np.array_equal(s['px'], before[e]['px']) and not obs_r[e].any()
+
+
+def test_waterworld_fp32_build_tracks_fp64_build():
+    from emu.driver import EmuWaterworld
+    cfg, E, T = WW["c2"], 4, 12
+    act = np.random.RandomState(3).randn(T, E, 5, 2) * 0.5
+    outs = []
+    for fp64 in (True, False):
+        eng = EmuWaterworld(E, seed=11, fp64=fp64, **cfg)
+        o0 = eng.reset()
+        outs.append((o0,) + eng.rollout(act, auto_reset=False))
+    assert outs[1][0].dtype == np.float32
+    assert np.abs(outs[0][0] - outs[1][0]).max() < 1e-5
+    same_events = np.array_equal(outs[0][4], outs[1][4])
+    if same_events:   # no threshold flipped in fp32: the trajectories stay within rounding noise
+        assert np.abs(outs[0][1] - outs[1][1]).max() < 1e-3
+
+
+# ------------------------------------------------------------------------------------ Pursuit
+def pool16():
+    return np.load(os.path.join(ROOT, "maps", "map_pool16.npy"))
+
+
+def small_map():
+    m = np.zeros((1, 5, 5), dtype=np.int32)
+    m[0, 2, 2] = -1
+    return m
+
+
+C3 = dict(n_evaders=30, n_pursuers=8, obs_range=7, surround=True, n_catch=2, flatten=True, reward_mech='local',
+          catchr=0.1, term_pursuit=5.0, sample_maps=True, include_id=True)
+PE = {
+    "c3": (pool16, C3),
+    "c3_global": (pool16, dict(C3, reward_mech='global', urgency_reward=-0.1)),
+    "ncatch": (pool16, dict(C3, surround=False, n_evaders=20, n_pursuers=12, obs_range=5)),
+    "window_r9": (pool16, dict(C3, constraint_window=0.5, n_evaders=6, n_pursuers=10, obs_range=9, include_id=False)),
+    "many_evaders": (pool16, dict(C3, n_evaders=50, n_pursuers=30, obs_range=11, catchr=0.01)),
+    "crowd": (small_map, dict(n_evaders=4, n_pursuers=10, obs_range=3, surround=True, reward_mech='local',
+                              catchr=0.1, term_pursuit=5.0)),
+    "conv_small": (small_map, dict(n_evaders=3, n_pursuers=3, obs_range=4, surround=False, n_catch=1,
+                                   reward_mech='global', flatten=False)),
+}
+
+
+def check_pursuit_state(eng, oracles):
+    for e, o in enumerate(oracles):
+        s = eng.state(e)
+        assert np.array_equal(s['pursuers'], o.ppos)
+        live = ~o.gone
+        assert np.array_equal(s['evaders'][live], o.epos[live])
+        assert [(s['gone'] >> j) & 1 for j in range(o.Ne)] == [int(x) for x in o.gone]
+        assert s['counter'] == o.rng.counter
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("name,E,T", [("c3", 5, 40), ("c3_global", 3, 30), ("ncatch", 5, 40), ("window_r9", 5, 40),
+                                      ("many_evaders", 2, 12), ("crowd", 6, 120), ("conv_small", 6, 80)])
+def test_pursuit_trajectories_bit_exact(variant, name, E, T):
+    from emu.driver import EmuPursuit
+    mk, cfg = PE[name]
+    maps = mk()
+    seed, base = 77, 500
+    eng = EmuPursuit(E, maps, seed=seed, env_id_base=base, defines=VARIANTS[variant], **cfg)
+    obs0 = eng.reset()
+    oracles = [PursuitOracle(maps, rng=Stream(seed, base + e), **cfg) for e in range(E)]
+    for e, o in enumerate(oracles):
+        assert np.array_equal(f32(o.reset()).reshape(obs0[e].shape), obs0[e]), e
+    check_pursuit_state(eng, oracles)
+    act = np.random.RandomState(9).randint(0, 5, size=(T, E, cfg['n_pursuers'])).astype(np.int32)
+    obs, rew, done, removed = eng.rollout(act, auto_reset=False)
+    total = 0
+    for t in range(T):
+        for e, o in enumerate(oracles):
+            oo, rr, dd, ii = o.step(act[t, e])
+            assert ii['removed'] == removed[t, e] and dd == bool(done[t, e]), (t, e)
+            assert np.array_equal(f32(oo).reshape(obs[t, e].shape), obs[t, e]), (t, e)
+            assert np.array_equal(f32(rr), rew[t, e]), (t, e)
+            total += ii['removed']
+    check_pursuit_state(eng, oracles)
+    if name in ("ncatch", "crowd"):
+        assert total > 0
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_pursuit_auto_reset(variant):
+    from emu.driver import EmuPursuit
+    mk, cfg = PE["crowd"]
+    maps, E, T, mpl, seed = mk(), 5, 40, 9, 3
+    eng = EmuPursuit(E, maps, seed=seed, max_path_length=mpl, defines=VARIANTS[variant], **cfg)
+    eng.reset()
+    act = np.random.RandomState(1).randint(0, 5, size=(T, E, cfg['n_pursuers'])).astype(np.int32)
+    obs, rew, done, removed = eng.rollout(act, auto_reset=True)
+    oracles = [PursuitOracle(maps, rng=Stream(seed, e), **cfg) for e in range(E)]
+    for o in oracles:
+        o.reset()
+    ts = np.zeros(E, int)
+    for t in range(T):
+        for e, o in enumerate(oracles):
+            oo, rr, dd, ii = o.step(act[t, e])
+            ts[e] += 1
+            dd = dd or ts[e] >= mpl
+            assert bool(done[t, e]) == dd and ii['removed'] == removed[t, e]
+            if dd:
+                oo = o.reset()
+                ts[e] = 0
+            assert np.array_equal(f32(oo).reshape(obs[t, e].shape), obs[t, e]), (t, e)
+            assert np.array_equal(f32(rr), rew[t, e])
+
+
+# ------------------------------------------------------------------------------------ Hostage
+HW = {
+    "c5": ((10, 16, 16, 4, 2), {}),
+    "c5_local": ((10, 16, 16, 4, 2), dict(reward_mech='local')),
+    "dense": ((3, 10, 5, 1, 2), dict(radius=0.05, sensor_range=0.35, key_radius=0.06, reward_mech='local', addid=False)),
+    "k12_fixed_key": ((4, 6, 8, 2, 1), dict(radius=0.04, n_sensors=12, key_radius=0.05, bomb_radius=0.02,
+                                            key_loc=np.array([[0.93, 0.97]]))),
+    "big": ((12, 40, 30, 2, 2), dict(radius=0.03, n_sensors=40, key_radius=0.04)),
+    "minimum": ((1, 1, 1, 1, 1), dict(n_sensors=1, radius=0.05, key_radius=0.05)),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("name,E,T,std", [("c5", 4, 50, 1.0), ("c5_local", 3, 50, 2.0), ("dense", 6, 150, 3.0),
+                                          ("k12_fixed_key", 6, 150, 3.0), ("big", 2, 12, 2.0),
+                                          ("minimum", 5, 80, 3.0)])
+def test_hostage_fp64_trajectories_match_oracle(variant, name, E, T, std):
+    from emu.driver import EmuHostage
+    args, kw = HW[name]
+    seed, base = 321, 77
+    eng = EmuHostage(E, *args, seed=seed, env_id_base=base, defines=VARIANTS[variant], **kw)
+    obs0 = eng.reset()
+    oracles = [HostageOracle(*args, rng=Stream(seed, base + e), **kw) for e in range(E)]
+    for e, o in enumerate(oracles):
+        assert np.abs(np.array(o.reset()) - obs0[e]).max() < 1e-9, e
+    act = np.random.RandomState(5).randn(T, E, args[0], 2) * std
+    obs, rew, done, info = eng.rollout(act, auto_reset=True)
+    for t in range(T):
+        for e, o in enumerate(oracles):
+            oo, rr, dd, ii = o.step(act[t, e])
+            assert [ii['ho_saved'], ii['cr_encs']] == list(info[t, e]), (t, e)
+            assert bool(done[t, e]) == dd, (t, e)
+            assert np.abs(rr - rew[t, e]).max() < 1e-9, (t, e)
+            if dd:                       # auto-reset: the slot holds the reset observation
+                oo = o.reset()
+            assert np.abs(np.array(oo) - obs[t, e]).max() < 1e-9, (t, e)
+    for e, o in enumerate(oracles):
+        s = eng.state(e)
+        assert s['counter'] == o.np_random.counter and s['t'] == o.t
+        assert np.array_equal(s['saved'], np.asarray(o.saved, bool))
