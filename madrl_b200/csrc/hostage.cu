@@ -66,6 +66,14 @@ __device__ __forceinline__ real unit_at(uint64_t seed, uint32_t env_id, uint64_t
 // the reward logic computes anyway, instead of a ballot + a 6-lane store per rescuer.
 #define MADRL_HW_DEFERRED_TAIL 1
 #endif
+#ifndef MADRL_HW_SPLIT
+// 1 (experiment): the rescuers live in their own four registers (lane i = rescuer i) and the
+// per-lane object registers hold only what is sensed and collided with -- criminals, then hostages.
+// Allies are never emitted (hw:395-397), so nothing is lost, and C5's 16 + 16 objects fit ONE chunk
+// of 32 lanes instead of two (10 rescuers + 32 objects = 42): one geometry / ballot / scan pass per
+// rescuer instead of two.  OPL then counts chunks of n_bad + n_hostages.
+#define MADRL_HW_SPLIT 0
+#endif
 #ifndef MADRL_HW_ONE_WARP_BLOCKS
 #define MADRL_HW_ONE_WARP_BLOCKS MADRL_ONE_WARP_BLOCKS   // see common.cuh
 #endif
@@ -89,12 +97,14 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
   const int warp_stride = gridDim.x * warps_per_block;
 #endif
   const int cLo = p.Nr, hLo = p.Nr + p.Nc, Nall = p.Nall;
+  // first object index held in the per-lane object registers (see MADRL_HW_SPLIT)
+  const int obase = MADRL_HW_SPLIT ? p.Nr : 0;
 
   real cull2_l[OPL], coll2_l[OPL];
   unsigned mC[OPL], mH[OPL];   // warp-uniform class masks (criminals, hostages) per object chunk
 #pragma unroll
   for (int c = 0; c < OPL; ++c) {
-    const int o = lane + 32 * c;
+    const int o = obase + lane + 32 * c;
     const bool isC = o >= cLo && o < hLo, isH = o >= hLo && o < Nall;
     cull2_l[c] = (isC || isH) ? p.cull2 : (real)-1;      // allies are sensed but never emitted (hw:395-397)
     coll2_l[c] = isC ? p.coll2_c : (isH ? p.coll2_h : (real)-1);
@@ -122,7 +132,7 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
     real* rec = p.objs + (size_t)e * 4 * Nall;
 #pragma unroll
     for (int c = 0; c < OPL; ++c) {
-      const int o = lane + 32 * c;
+      const int o = obase + lane + 32 * c;
       const bool v = o < Nall;
       x[c] = v ? rec[o] : (real)0;
       y[c] = v ? rec[Nall + o] : (real)0;
@@ -131,6 +141,12 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
       col[c] = 0u;
       sav[c] = (o >= hLo && o < Nall) ? (p.saved[(size_t)e * p.Nh + (o - hLo)] != 0) : false;
     }
+#if MADRL_HW_SPLIT
+    real rpx = 0, rpy = 0, rpvx = 0, rpvy = 0;   // rescuer `lane`
+    if (lane < p.Nr) { rpx = rec[lane]; rpy = rec[Nall + lane]; rpvx = rec[2 * Nall + lane]; rpvy = rec[3 * Nall + lane]; }
+#else
+    real &rpx = x[0], &rpy = y[0], &rpvx = vx[0], &rpvy = vy[0];   // rescuers are objects 0..Nr-1 of chunk 0
+#endif
     real kx = p.fixed[4 * (size_t)e], ky = p.fixed[4 * (size_t)e + 1];
     real bx = p.fixed[4 * (size_t)e + 2], by = p.fixed[4 * (size_t)e + 3];
     int flags = p.flags[e];
@@ -165,11 +181,20 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
             }
           } else { kx = p.key_x; ky = p.key_y; }
           flags = 4;   // gate closed, not bombed, key known
+#if MADRL_HW_SPLIT
+          if (lane < p.Nr) {                                                 // hw:155-159
+            const uint64_t b = n + 2 * (uint64_t)lane;
+            rpx = unit_at<real>(p.seed, env_id, b);
+            const real yy = unit_at<real>(p.seed, env_id, b + 1);
+            rpy = yy < (real)0.55 ? (real)0.55 : (yy > (real)0.95 ? (real)0.95 : yy);
+            rpvx = 0; rpvy = 0;
+          }
+#endif
 #pragma unroll
           for (int c = 0; c < OPL; ++c) {
-            const int o = lane + 32 * c;
+            const int o = obase + lane + 32 * c;
             sav[c] = false;
-            if (o < cLo) {                                                   // hw:155-159
+            if (!MADRL_HW_SPLIT && o < cLo) {                                // hw:155-159
               const uint64_t b = n + 2 * (uint64_t)o;
               x[c] = unit_at<real>(p.seed, env_id, b);
               const real yy = unit_at<real>(p.seed, env_id, b + 1);
@@ -207,19 +232,19 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
           real sq = 0;
           if (lane < p.Nr) {
             const real ax = act.x * p.action_scale, ay = act.y * p.action_scale;
-            vx[0] += ax; vy[0] += ay;
-            x[0] += vx[0]; y[0] += vy[0];
+            rpvx += ax; rpvy += ay;
+            rpx += rpvx; rpy += rpvy;
             sq = ax * ax + ay * ay;
-            real cx = clip01(x[0]), cy = clip01(y[0]);
-            if (x[0] != cx) vx[0] = 0;
-            if (y[0] != cy) vy[0] = 0;
-            x[0] = cx; y[0] = cy;
+            real cx = clip01(rpx), cy = clip01(rpy);
+            if (rpx != cx) rpvx = 0;
+            if (rpy != cy) rpvy = 0;
+            rpx = cx; rpy = cy;
             if (!gate_pre) {
-              cx = x[0] < p.gate_lo ? p.gate_lo : (x[0] > (real)1 ? (real)1 : x[0]);
-              cy = y[0] < p.gate_lo ? p.gate_lo : (y[0] > (real)1 ? (real)1 : y[0]);
-              if (x[0] != cx) vx[0] = -vx[0];
-              if (y[0] != cy) vy[0] = -vy[0];
-              x[0] = cx; y[0] = cy;
+              cx = rpx < p.gate_lo ? p.gate_lo : (rpx > (real)1 ? (real)1 : rpx);
+              cy = rpy < p.gate_lo ? p.gate_lo : (rpy > (real)1 ? (real)1 : rpy);
+              if (rpx != cx) rpvx = -rpvx;
+              if (rpy != cy) rpvy = -rpvy;
+              rpx = cx; rpy = cy;
             }
           }
           pen = p.control_penalty * (p.reward_global ? hw_warp_sum(sq) : sq);
@@ -228,7 +253,7 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
         //      gate flag): hw:286-296 ----------------------------------------------------------------
         unsigned coll_ke, coll_bo;
         {
-          const real dkx = x[0] - kx, dky = y[0] - ky, dbx = x[0] - bx, dby = y[0] - by;
+          const real dkx = rpx - kx, dky = rpy - ky, dbx = rpx - bx, dby = rpy - by;
           coll_ke = __ballot_sync(FULL_MASK, lane < p.Nr && dkx * dkx + dky * dky <= p.coll2_key);
           coll_bo = __ballot_sync(FULL_MASK, lane < p.Nr && dbx * dbx + dby * dby <= p.coll2_bomb);
         }
@@ -236,8 +261,8 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
         // ---- sense: one rescuer at a time -----------------------------------------------------------
         real* obs_row = obs_t;
         for (int pi = 0; pi < p.Nr; ++pi, obs_row += p.D) {
-          const real mx = __shfl_sync(FULL_MASK, x[0], pi), my = __shfl_sync(FULL_MASK, y[0], pi);
-          const real mvx = __shfl_sync(FULL_MASK, vx[0], pi), mvy = __shfl_sync(FULL_MASK, vy[0], pi);
+          const real mx = __shfl_sync(FULL_MASK, rpx, pi), my = __shfl_sync(FULL_MASK, rpy, pi);
+          const real mvx = __shfl_sync(FULL_MASK, rpvx, pi), mvy = __shfl_sync(FULL_MASK, rpvy, pi);
           const real krx = kx - mx, kry = ky - my, kd2 = krx * krx + kry * kry;
           const real brx = bx - mx, bry = by - my, bd2 = brx * brx + bry * bry;
           real bK[KCH], bB[KCH], bC[KCH], bH[KCH];
@@ -428,10 +453,13 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
     }
 #pragma unroll
     for (int c = 0; c < OPL; ++c) {
-      const int o = lane + 32 * c;
+      const int o = obase + lane + 32 * c;
       if (o < Nall) { rec[o] = x[c]; rec[Nall + o] = y[c]; rec[2 * Nall + o] = vx[c]; rec[3 * Nall + o] = vy[c]; }
       if (o >= hLo && o < Nall) p.saved[(size_t)e * p.Nh + (o - hLo)] = sav[c] ? 1 : 0;
     }
+#if MADRL_HW_SPLIT
+    if (lane < p.Nr) { rec[lane] = rpx; rec[Nall + lane] = rpy; rec[2 * Nall + lane] = rpvx; rec[3 * Nall + lane] = rpvy; }
+#endif
     if (lane == 0) {
       p.fixed[4 * (size_t)e] = kx; p.fixed[4 * (size_t)e + 1] = ky;
       p.fixed[4 * (size_t)e + 2] = bx; p.fixed[4 * (size_t)e + 3] = by;
@@ -626,7 +654,7 @@ static int hw_launch(madrl_hostage* h, int mode, int T, const void* actions, voi
   p.ctr = (uint64_t*)(st + h->lay.rng_counter); p.sensors = (const real*)(st + h->lay.sensors);
   p.actions = (const real*)actions; p.obs = (real*)obs; p.rew = (real*)rew;
   p.done = done; p.info = info; p.mask = mask;
-  const int opl = (p.Nall + 31) / 32, kch = (p.K + 31) / 32;
+  const int opl = ((MADRL_HW_SPLIT ? p.Nall - p.Nr : p.Nall) + 31) / 32, kch = (p.K + 31) / 32;
 #define MADRL_HW_CASE(O, KH, KC_) return hw_launch_inst<real, O, KH, KC_>(h, p, stream)
   if (p.K == 30) {
     if (opl == 1) MADRL_HW_CASE(1, 1, 30);
