@@ -36,6 +36,9 @@ def run(E, T, args=(10, 16, 16, 4, 2), reps=5, mpl=0):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "quick":
+        run(8192, 32)
+        sys.exit(0)
     run(8192, 32)
     run(4096, 64)
     run(65536, 8)

@@ -41,6 +41,9 @@ def run(E, T, wpb=0, bps=0, cfg=C3, reps=5, mpl=500):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "quick":
+        run(65536, 32)
+        sys.exit(0)
     for wpb in (4, 2):
         run(65536, 8, wpb)
     run(65536, 32)
