@@ -261,3 +261,75 @@ def test_hostage_fp64_trajectories_match_oracle(variant, name, E, T, std):
         s = eng.state(e)
         assert s['counter'] == o.np_random.counter and s['t'] == o.t
         assert np.array_equal(s['saved'], np.asarray(o.saved, bool))
+
+
+# ------------------------------------------------------------------ golden vectors of the REAL reference
+# (tests/golden/*.npz, recorded by oracle/make_golden.py from the imported reference classes)
+def _golden(name):
+    import json
+    from conftest import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    return g, json.loads(str(g["config"]))
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("name", ["ww_c2", "ww_dense", "ww_c4", "ww_global_nospeed"])
+def test_waterworld_reproduces_reference_golden(variant, name):
+    from emu.driver import EmuWaterworld
+    g, cfg = _golden(name)
+    if cfg.get("obstacle_loc", 0) is not None and "obstacle_loc" in cfg:
+        cfg["obstacle_loc"] = np.array(cfg["obstacle_loc"])
+    eng = EmuWaterworld(1, seed=int(g["seed"]), env_id_base=int(g["env_id"]), defines=VARIANTS[variant], **cfg)
+    assert np.abs(eng.reset()[0] - g["obs0"]).max() < 1e-9
+    obs, rew, done, info = eng.rollout(g["actions"][:, None], auto_reset=False)
+    assert np.array_equal(info[:, 0], g["info"])
+    assert np.abs(obs[:, 0] - g["obs"]).max() < 1e-9
+    assert np.abs(rew[:, 0] - g["rew"]).max() < 1e-9
+    assert np.array_equal(done[:, 0].astype(bool), g["done"])
+    assert eng.state(0)['counter'] == int(g["counter"])
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("name", ["pe_c3", "pe_c3_global", "pe_ncatch", "pe_window", "pe_small", "pe_even_range",
+                                  "pe_crowd"])
+def test_pursuit_reproduces_reference_golden(variant, name):
+    from emu.driver import EmuPursuit
+    g, cfg = _golden(name)
+    maps = pool16() if str(g["maps"]) == "pool16" else small_map()
+    eng = EmuPursuit(1, maps, seed=int(g["seed"]), env_id_base=int(g["env_id"]), defines=VARIANTS[variant], **cfg)
+    assert np.array_equal(eng.reset()[0], f32(g["obs0"]))
+    resets = list(g["reset_at"])
+    t0, k, T = 0, 0, g["actions"].shape[0]
+    while t0 < T:                      # segment by segment between the recorded reset() calls
+        t1 = (resets[k] + 1) if k < len(resets) else T
+        obs, rew, done, removed = eng.rollout(g["actions"][t0:t1, None], auto_reset=False)
+        assert np.array_equal(obs[:, 0], f32(g["obs"][t0:t1]))
+        assert np.array_equal(rew[:, 0], f32(g["rew"][t0:t1]))
+        assert np.array_equal(done[:, 0].astype(bool), g["done"][t0:t1])
+        assert np.array_equal(removed[:, 0], g["removed"][t0:t1])
+        if k < len(resets):
+            assert np.array_equal(eng.reset()[0], f32(g["reset_obs"][k]))
+            k += 1
+        t0 = t1
+    assert eng.state(0)['counter'] == int(g["counter"])
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("name", ["hw_c5", "hw_c5_local", "hw_dense", "hw_k12"])
+def test_hostage_reproduces_reference_golden(variant, name):
+    from emu.driver import EmuHostage
+    g, kw = _golden(name)
+    if 'key_loc' in kw:
+        kw['key_loc'] = np.array(kw['key_loc'])
+    args = tuple(int(a) for a in g["args"])
+    eng = EmuHostage(1, *args, seed=int(g["seed"]), env_id_base=int(g["env_id"]), defines=VARIANTS[variant], **kw)
+    assert np.abs(eng.reset()[0] - g["obs0"]).max() < 1e-9
+    obs, rew, done, info = eng.rollout(g["actions"][:, None], auto_reset=True)
+    assert np.array_equal(info[:, 0], g["info"])
+    assert np.array_equal(done[:, 0].astype(bool), g["done"])
+    assert np.abs(rew[:, 0] - g["rew"]).max() < 1e-9
+    expect = g["obs"].copy()
+    for k, t in enumerate(g["reset_at"]):          # the reference driver reset() where done
+        expect[t] = g["reset_obs"][k]
+    assert np.abs(obs[:, 0] - expect).max() < 1e-9
+    assert eng.state(0)['counter'] == int(g["counter"])
