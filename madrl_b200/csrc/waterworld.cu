@@ -128,6 +128,9 @@ __device__ __noinline__ Spawn<real> spawn_object(uint64_t seed, uint32_t env_id,
 #ifndef MADRL_WW_ONE_WARP_BLOCKS
 #define MADRL_WW_ONE_WARP_BLOCKS MADRL_ONE_WARP_BLOCKS   // see common.cuh
 #endif
+#ifndef MADRL_WW_SKIP_EMPTY_CATCH
+#define MADRL_WW_SKIP_EMPTY_CATCH 0   // 1 (experiment): skip catches / respawn / mask reductions on steps without any collision
+#endif
 #ifndef MADRL_WW_SMEM_MIN_OPL
 // Kernels with at least this many objects per lane stage the objects that survive the range cull
 // in per-warp shared memory slots (ascending object order): the sensor lanes then walk the slots
@@ -510,6 +513,13 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
         // ---- catches, respawn, rewards: ww:285,293,358-385 -----------------------------------------
         unsigned whoE = 0u, whoP = 0u, whoEnc = 0u;
         int nE = 0, nP = 0, nEnc = 0;
+#if MADRL_WW_SKIP_EMPTY_CATCH
+        // most steps nobody touches anything: one ballot decides whether the catch logic runs at all
+        bool touched = false;
+#pragma unroll
+        for (int c = 0; c < OPL; ++c) touched |= col[c] != 0u;
+        if (__ballot_sync(FULL_MASK, touched) != 0u) {
+#endif
 #pragma unroll
         for (int c = 0; c < OPL; ++c) {
           const int cnt = __popc(col[c]);
@@ -536,6 +546,9 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
         whoE = __reduce_or_sync(FULL_MASK, whoE);
         whoP = __reduce_or_sync(FULL_MASK, whoP);
         whoEnc = __reduce_or_sync(FULL_MASK, whoEnc);
+#if MADRL_WW_SKIP_EMPTY_CATCH
+        }
+#endif
 #if MADRL_WW_DEFERRED_TAIL
         // ww:411-428 tail of every pursuer's row: [touched an evader, touched a poison, id]; lane i
         // writes pursuer i's.  whoEnc / whoP are exactly the any-collision masks (ww:376, ww:293).

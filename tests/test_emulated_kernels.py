@@ -21,7 +21,8 @@ pytestmark = pytest.mark.skipif(shutil.which(os.environ.get("CXX", "g++")) is No
 # build variants: the product defaults, and every experiment flag that is still off in the product
 VARIANTS = {
     "default": (),
-    "experiments": ("-DMADRL_ONE_WARP_BLOCKS=1", "-DMADRL_WW_SMEM_MIN_OPL=1", "-DMADRL_HW_SPLIT=1"),
+    "experiments": ("-DMADRL_ONE_WARP_BLOCKS=1", "-DMADRL_WW_SMEM_MIN_OPL=1", "-DMADRL_HW_SPLIT=1",
+                    "-DMADRL_WW_SKIP_EMPTY_CATCH=1"),
 }
 
 
