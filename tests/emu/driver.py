@@ -149,8 +149,9 @@ class EmuWaterworld(_Engine):
         objs = self.view(Ly.objs, self.obs_dtype, (self.n_envs, 4, N))[e].astype(np.float64)
         X, V = objs[0:2].T, objs[2:4].T
         Np, Ne = self.n_pursuers, self.n_evaders
+        obst = self.view(Ly.obst, self.obs_dtype, (self.n_envs, 2))[e].astype(np.float64)[None]
         return dict(px=X[:Np], pv=V[:Np], ex=X[Np:Np + Ne], ev=V[Np:Np + Ne], ox=X[Np + Ne:], ov=V[Np + Ne:],
-                    t=int(self.view(Ly.timestep, np.int32, (self.n_envs,))[e]),
+                    obst=obst, t=int(self.view(Ly.timestep, np.int32, (self.n_envs,))[e]),
                     counter=int(self.view(Ly.rng_counter, np.int64, (self.n_envs,))[e]))
 
 

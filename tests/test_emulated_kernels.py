@@ -131,6 +131,42 @@ def test_waterworld_fp32_build_tracks_fp64_build():
         assert np.abs(outs[0][1] - outs[1][1]).max() < 1e-3
 
 
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("name,E,T,min_frac", [("c2", 12, 12, 0.85), ("dense", 10, 12, 0.85), ("c4", 2, 4, 0.3)])
+def test_waterworld_fp32_single_step_teacher_forced(variant, name, E, T, min_frac):
+    """The fp32 instantiation, one step at a time from its own fp32 states, against the float64 oracle
+    (tolerance 1e-5, transitions with a comparison within 3e-7 of its threshold skipped) -- the
+    GPU test's methodology at small size."""
+    from emu.driver import EmuWaterworld
+    from oracle.waterworld_oracle import fragile_step
+    cfg, seed = WW[name], 99
+    eng = EmuWaterworld(E, seed=seed, fp64=False, defines=VARIANTS[variant], **cfg)
+    eng.reset()
+    Np = cfg['n_pursuers']
+    rs = np.random.RandomState(3)
+    orc = WaterworldOracle(rng=Stream(seed, 0), **cfg)
+    checked = 0
+    for t in range(T):
+        act = (rs.randn(1, E, Np, 2) * 0.7).astype(np.float32)
+        pre = [eng.state(e) for e in range(E)]
+        obs, rew, done, info = eng.rollout(act, auto_reset=False)
+        for e in range(E):
+            if fragile_step(orc, pre[e], act[0, e], 3e-7):
+                continue
+            orc.np_random = Stream(seed, e, counter=pre[e]['counter'])
+            orc.set_state(pre[e])
+            oo, rr, dd, ii = orc.step(act[0, e].astype(np.float64))
+            assert [ii['evcatches'], ii['pocatches']] == list(info[0, e]), (t, e)
+            assert np.abs(np.array(oo) - obs[0, e]).max() <= 1e-5, (t, e)
+            assert np.abs(rr - rew[0, e]).max() <= 1e-5, (t, e)
+            post = eng.state(e)
+            assert post['counter'] == orc.np_random.counter
+            for k in ('px', 'pv', 'ex', 'ev', 'ox', 'ov'):
+                assert np.abs(post[k] - getattr(orc, k)).max() <= 1e-5, (t, e, k)
+            checked += 1
+    assert checked > min_frac * E * T, checked
+
+
 # ------------------------------------------------------------------------------------ Pursuit
 def pool16():
     return np.load(os.path.join(ROOT, "maps", "map_pool16.npy"))
