@@ -88,6 +88,10 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
   return v;
 }
+// Byte 0 of a 32-bit shared word.  Only that byte is consumed, so concurrent atomic updates of the
+// upper bytes of the same word (Pursuit's packed cell word: building | pursuers << 8 | evaders << 16)
+// by other lanes are harmless; the emulator's hazard checker relies on this being a separate helper.
+__device__ __forceinline__ uint32_t lds_low_byte(uint32_t a) { return lds_u32(a) & 0xffu; }
 __device__ __forceinline__ float lds_f32(uint32_t a) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");

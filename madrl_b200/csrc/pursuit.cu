@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(128, MADRL_PE_MINBLOCKS) pe_kernel(const __gri
             const int nx = px + dx, ny = py + dy;
             const uint32_t cur = cell_a + 4u * (px * ys + py), nxt = cell_a + 4u * (nx * ys + ny);
             if ((unsigned)a < 4u && (unsigned)nx < (unsigned)xs && (unsigned)ny < (unsigned)ys &&
-                (lds_u32(cur) & 0xff) == 0u && (lds_u32(nxt) & 0xff) == 0u) {
+                lds_low_byte(cur) == 0u && lds_low_byte(nxt) == 0u) {
               reds_add_u32(cur, 0u - (1u << 8));
               reds_add_u32(nxt, 1u << 8);
               px = nx; py = ny;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(128, MADRL_PE_MINBLOCKS) pe_kernel(const __gri
               const int nx = ex[c] + dx, ny = ey[c] + dy;
               const uint32_t cur = cell_a + 4u * (ex[c] * ys + ey[c]), nxt = cell_a + 4u * (nx * ys + ny);
               if (a < 4 && (unsigned)nx < (unsigned)xs && (unsigned)ny < (unsigned)ys &&
-                  (lds_u32(cur) & 0xff) == 0u && (lds_u32(nxt) & 0xff) == 0u) {
+                  lds_low_byte(cur) == 0u && lds_low_byte(nxt) == 0u) {
                 reds_add_u32(cur, 0u - (1u << 16));
                 reds_add_u32(nxt, 1u << 16);
                 ex[c] = nx; ey[c] = ny;

@@ -23,9 +23,21 @@ def load(defines=()):
     return _libs[key]
 
 
+def races(reset=True):
+    """Shared-memory hazards (see smem_access in tests/emu/include/cuda_runtime.h) reported by every
+    loaded emulator library since the last call."""
+    n = 0
+    for lib in _libs.values():
+        n += int(lib.madrl_emu_race_count())
+        if reset:
+            lib.madrl_emu_race_reset()
+    return n
+
+
 def _declare(lib):
     vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
     lib.madrl_last_error.restype = C.c_char_p
+    lib.madrl_emu_race_count.restype = C.c_long
     for fam, cfg, lay in (("ww", L.WWConfig, L.WWLayout), ("hostage", L.HWConfig, L.HWLayout),
                           ("pursuit", L.PEConfig, L.PELayout)):
         g = lambda n: getattr(lib, "madrl_%s_%s" % (fam, n))   # noqa: E731

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <ucontext.h>
 
+#include <unordered_map>
 #include <vector>
 
 uint3 threadIdx, blockIdx;
@@ -39,8 +40,31 @@ struct Fiber {
   char* stack = nullptr;
   bool done = false;
   long warp_phase = 0, block_phase = 0;
+  long syncs = 0;              // __syncwarp / __syncthreads passed: the memory-ordering epoch
   unsigned tid = 0;
 };
+
+// per shared-memory byte: who touched it in which epoch (see smem_access)
+struct Shadow {
+  long w_epoch = -1, r_epoch = -1, a_epoch = -1;
+  int w_tid = -1;
+  uint64_t r_tids_lo = 0, r_tids_hi = 0, a_tids_lo = 0, a_tids_hi = 0;   // up to 128 threads per block
+};
+std::unordered_map<uint32_t, Shadow> g_shadow;
+long g_races = 0;
+
+inline void bit_set(uint64_t& lo, uint64_t& hi, unsigned t) { (t < 64 ? lo : hi) |= 1ull << (t & 63); }
+inline bool others(uint64_t lo, uint64_t hi, unsigned t) {
+  uint64_t l = lo, h = hi;
+  (t < 64 ? l : h) &= ~(1ull << (t & 63));
+  return (l | h) != 0;
+}
+
+void report(const char* what, uint32_t addr, unsigned tid, long epoch) {
+  if (++g_races <= 8)
+    fprintf(stderr, "madrl_emu: shared-memory %s hazard at offset %u: thread %u (block %u), no __syncwarp/__syncthreads since the conflicting access (epoch %ld)\n",
+            what, addr, tid, blockIdx.x, epoch);
+}
 
 std::vector<Fiber> g_fibers;
 std::vector<Rendezvous> g_warps;
@@ -66,6 +90,40 @@ void fiber_entry() {
 }  // namespace
 
 unsigned char* smem_anchor() { return madrl::ww_smem; }
+
+void note_sync() { ++g_fibers[g_cur].syncs; }
+
+extern "C" long madrl_emu_race_count() { return g_races; }
+extern "C" void madrl_emu_race_reset() { g_races = 0; }
+
+void smem_access(uint32_t addr, uint32_t bytes, SmemKind kind) {
+  const Fiber& f = g_fibers[g_cur];
+  const long e = f.syncs;
+  const unsigned t = f.tid;
+  for (uint32_t b = 0; b < bytes; ++b) {
+    Shadow& s = g_shadow[addr + b];
+    const bool w_conf = s.w_epoch == e && s.w_tid != (int)t;
+    const bool r_conf = s.r_epoch == e && others(s.r_tids_lo, s.r_tids_hi, t);
+    const bool a_conf = s.a_epoch == e && others(s.a_tids_lo, s.a_tids_hi, t);
+    if (kind == SMEM_READ) {
+      if (w_conf) { report("read-after-write", addr + b, t, e); }
+      else if (a_conf) { report("read-vs-atomic", addr + b, t, e); }
+      if (s.r_epoch != e) { s.r_epoch = e; s.r_tids_lo = s.r_tids_hi = 0; }
+      bit_set(s.r_tids_lo, s.r_tids_hi, t);
+    } else if (kind == SMEM_WRITE) {
+      if (w_conf) { report("write-after-write", addr + b, t, e); }
+      else if (r_conf) { report("write-after-read", addr + b, t, e); }
+      else if (a_conf) { report("write-vs-atomic", addr + b, t, e); }
+      s.w_epoch = e; s.w_tid = (int)t;
+    } else {
+      if (w_conf) { report("atomic-vs-write", addr + b, t, e); }
+      else if (r_conf) { report("atomic-vs-read", addr + b, t, e); }
+      if (s.a_epoch != e) { s.a_epoch = e; s.a_tids_lo = s.a_tids_hi = 0; }
+      bit_set(s.a_tids_lo, s.a_tids_hi, t);
+    }
+    if (w_conf || r_conf || a_conf) break;   // one report per access
+  }
+}
 
 void check_smem(size_t bytes) {
   if (bytes > madrl::kEmuSmemBytes) {
@@ -111,6 +169,7 @@ void run_grid(unsigned grid, unsigned block, size_t smem, const std::function<vo
     // uninitialised shared memory must not be relied upon: poison it
     memset(madrl::ww_smem, 0xCD, madrl::kEmuSmemBytes);
     memset(madrl::smem_u32, 0xCD, madrl::kEmuSmemBytes);
+    g_shadow.clear();
     g_fibers.assign(block, Fiber());
     g_warps.assign(block / 32, Rendezvous());
     g_block = Rendezvous();

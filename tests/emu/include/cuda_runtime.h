@@ -88,6 +88,17 @@ const uint64_t* warp_exchange(uint64_t v);
 void block_barrier();
 void run_grid(unsigned grid, unsigned block, size_t smem, const std::function<void()>& body);
 unsigned char* smem_anchor();   // origin of the 32-bit "shared addresses"
+// Shared-memory hazard checker: every access through the helpers below is recorded per byte with
+// the accessing lane and the number of __syncwarp/__syncthreads it has passed; two accesses to the
+// same byte by different lanes, at least one a plain write (or a plain access vs an atomic), with no
+// such barrier in between are a race on real hardware (lanes are not lock-step) even though the
+// fiber schedule happens to order them.  Collectives other than __syncwarp/__syncthreads do not order
+// memory.  Reports are counted and the first few printed; tests read the count.
+enum SmemKind { SMEM_READ = 0, SMEM_WRITE = 1, SMEM_ATOMIC = 2 };
+void smem_access(uint32_t addr, uint32_t bytes, SmemKind kind);
+void note_sync();                // called by __syncwarp / __syncthreads of the current lane
+extern "C" long madrl_emu_race_count();
+extern "C" void madrl_emu_race_reset();
 void check_smem(size_t bytes);
 
 template <typename K, typename... A>
@@ -134,8 +145,8 @@ static inline unsigned __reduce_or_sync(unsigned, unsigned v) {
   for (int i = 0; i < 32; ++i) m |= (unsigned)s[i];
   return m;
 }
-static inline void __syncwarp(unsigned = 0xffffffffu) { madrl_emu::warp_exchange(0); }
-static inline void __syncthreads() { madrl_emu::block_barrier(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { madrl_emu::warp_exchange(0); madrl_emu::note_sync(); }
+static inline void __syncthreads() { madrl_emu::block_barrier(); madrl_emu::note_sync(); }
 
 // CUDA's global min / max overloads
 static inline int min(int a, int b) { return a < b ? a : b; }
@@ -163,12 +174,19 @@ static inline char* emu_at(uint32_t a) { return reinterpret_cast<char*>(madrl_em
 static inline uint32_t smem_addr(const void* p) {
   return (uint32_t)(reinterpret_cast<const char*>(p) - reinterpret_cast<const char*>(madrl_emu::smem_anchor()));
 }
-static inline uint32_t lds_u32(uint32_t a) { uint32_t v; memcpy(&v, emu_at(a), 4); return v; }
-static inline float lds_f32(uint32_t a) { float v; memcpy(&v, emu_at(a), 4); return v; }
-static inline uint32_t lds_u16(uint32_t a) { uint16_t v; memcpy(&v, emu_at(a), 2); return v; }
-static inline void sts_u32(uint32_t a, uint32_t v) { memcpy(emu_at(a), &v, 4); }
-static inline void sts_u16(uint32_t a, uint32_t v) { const uint16_t h = (uint16_t)v; memcpy(emu_at(a), &h, 2); }
-static inline void reds_add_u32(uint32_t a, uint32_t v) { sts_u32(a, lds_u32(a) + v); }
+using madrl_emu::smem_access;
+using madrl_emu::SMEM_READ; using madrl_emu::SMEM_WRITE; using madrl_emu::SMEM_ATOMIC;
+static inline uint32_t lds_u32(uint32_t a) { smem_access(a, 4, SMEM_READ); uint32_t v; memcpy(&v, emu_at(a), 4); return v; }
+static inline uint32_t lds_low_byte(uint32_t a) { smem_access(a, 1, SMEM_READ); return *reinterpret_cast<unsigned char*>(emu_at(a)); }
+static inline float lds_f32(uint32_t a) { smem_access(a, 4, SMEM_READ); float v; memcpy(&v, emu_at(a), 4); return v; }
+static inline uint32_t lds_u16(uint32_t a) { smem_access(a, 2, SMEM_READ); uint16_t v; memcpy(&v, emu_at(a), 2); return v; }
+static inline void sts_u32(uint32_t a, uint32_t v) { smem_access(a, 4, SMEM_WRITE); memcpy(emu_at(a), &v, 4); }
+static inline void sts_u16(uint32_t a, uint32_t v) { smem_access(a, 2, SMEM_WRITE); const uint16_t h = (uint16_t)v; memcpy(emu_at(a), &h, 2); }
+static inline void reds_add_u32(uint32_t a, uint32_t v) {
+  const uint32_t first = v ? (uint32_t)__builtin_ctz(v) / 8u : 0u;   // bytes below the lowest set bit of v never change
+  smem_access(a + first, 4 - first, SMEM_ATOMIC);
+  uint32_t w; memcpy(&w, emu_at(a), 4); w += v; memcpy(emu_at(a), &w, 4);
+}
 static inline void prefetch_l1(const void*) {}
 static inline unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
 
@@ -177,26 +195,28 @@ template <> struct CandSlot<float> {
   static constexpr uint32_t kStride = 32;
   static inline void put(uint32_t a, float rx, float ry, float d2, float vx, float vy) {
     const float q[6] = {rx, ry, d2, d2, vx, vy};
+    smem_access(a, sizeof q, SMEM_WRITE);
     memcpy(emu_at(a), q, sizeof q);
   }
   static inline void geom(uint32_t a, float& rx, float& ry, float& d2) {
-    float q[3]; memcpy(q, emu_at(a), sizeof q); rx = q[0]; ry = q[1]; d2 = q[2];
+    float q[3]; smem_access(a, sizeof q, SMEM_READ); memcpy(q, emu_at(a), sizeof q); rx = q[0]; ry = q[1]; d2 = q[2];
   }
   static inline void vel(uint32_t a, float& vx, float& vy) {
-    float q[2]; memcpy(q, emu_at(a + 16), sizeof q); vx = q[0]; vy = q[1];
+    float q[2]; smem_access(a + 16, sizeof q, SMEM_READ); memcpy(q, emu_at(a + 16), sizeof q); vx = q[0]; vy = q[1];
   }
 };
 template <> struct CandSlot<double> {
   static constexpr uint32_t kStride = 48;
   static inline void put(uint32_t a, double rx, double ry, double d2, double vx, double vy) {
     const double q[6] = {rx, ry, d2, 0.0, vx, vy};
+    smem_access(a, sizeof q, SMEM_WRITE);
     memcpy(emu_at(a), q, sizeof q);
   }
   static inline void geom(uint32_t a, double& rx, double& ry, double& d2) {
-    double q[3]; memcpy(q, emu_at(a), sizeof q); rx = q[0]; ry = q[1]; d2 = q[2];
+    double q[3]; smem_access(a, sizeof q, SMEM_READ); memcpy(q, emu_at(a), sizeof q); rx = q[0]; ry = q[1]; d2 = q[2];
   }
   static inline void vel(uint32_t a, double& vx, double& vy) {
-    double q[2]; memcpy(q, emu_at(a + 32), sizeof q); vx = q[0]; vy = q[1];
+    double q[2]; smem_access(a + 32, sizeof q, SMEM_READ); memcpy(q, emu_at(a + 32), sizeof q); vx = q[0]; vy = q[1];
   }
 };
 }  // namespace madrl

@@ -30,6 +30,16 @@ def f32(x):
     return np.asarray(x, dtype=np.float64).astype(np.float32)
 
 
+@pytest.fixture(autouse=True)
+def no_shared_memory_hazards():
+    """Every emulated launch is also race-checked: two lanes touching the same shared-memory byte,
+    one of them writing, without a __syncwarp / __syncthreads in between, fail the test."""
+    from emu import driver
+    driver.races()
+    yield
+    assert driver.races() == 0, "shared-memory hazard reported by the emulator (see stderr)"
+
+
 # ------------------------------------------------------------------------------------ Waterworld
 WW = {
     "c2": dict(n_pursuers=5, n_evaders=5),
