@@ -23,7 +23,10 @@ VARIANTS = {
     "default": (),
     "experiments": ("-DMADRL_ONE_WARP_BLOCKS=1", "-DMADRL_WW_SMEM_MIN_OPL=1", "-DMADRL_HW_SPLIT=1",
                     "-DMADRL_WW_SKIP_EMPTY_CATCH=1"),
+    # the same experiments on the default 4-warp blocks (per-warp shared-memory regions)
+    "experiments_4warp": ("-DMADRL_WW_SMEM_MIN_OPL=1", "-DMADRL_HW_SPLIT=1", "-DMADRL_WW_SKIP_EMPTY_CATCH=1"),
 }
+PE_VARIANTS = ["default", "experiments"]   # the 4-warp experiment flags do not touch the Pursuit kernel
 
 
 def f32(x):
@@ -213,7 +216,7 @@ def check_pursuit_state(eng, oracles):
         assert s['counter'] == o.rng.counter
 
 
-@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("variant", PE_VARIANTS)
 @pytest.mark.parametrize("name,E,T", [("c3", 5, 40), ("c3_global", 3, 30), ("ncatch", 5, 40), ("window_r9", 5, 40),
                                       ("many_evaders", 2, 12), ("crowd", 6, 120), ("conv_small", 6, 80)])
 def test_pursuit_trajectories_bit_exact(variant, name, E, T):
@@ -242,7 +245,7 @@ def test_pursuit_trajectories_bit_exact(variant, name, E, T):
         assert total > 0
 
 
-@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("variant", PE_VARIANTS)
 def test_pursuit_auto_reset(variant):
     from emu.driver import EmuPursuit
     mk, cfg = PE["crowd"]
@@ -336,7 +339,7 @@ def test_waterworld_reproduces_reference_golden(variant, name):
     assert eng.state(0)['counter'] == int(g["counter"])
 
 
-@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("variant", PE_VARIANTS)
 @pytest.mark.parametrize("name", ["pe_c3", "pe_c3_global", "pe_ncatch", "pe_window", "pe_small", "pe_even_range",
                                   "pe_crowd"])
 def test_pursuit_reproduces_reference_golden(variant, name):
