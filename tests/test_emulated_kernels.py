@@ -22,11 +22,12 @@ pytestmark = pytest.mark.skipif(shutil.which(os.environ.get("CXX", "g++")) is No
 VARIANTS = {
     "default": (),
     "experiments": ("-DMADRL_ONE_WARP_BLOCKS=1", "-DMADRL_WW_SMEM_MIN_OPL=1", "-DMADRL_HW_SPLIT=1",
-                    "-DMADRL_WW_SKIP_EMPTY_CATCH=1"),
+                    "-DMADRL_WW_SKIP_EMPTY_CATCH=1", "-DMADRL_PE_PHILOX_CACHE=1"),
     # the same experiments on the default 4-warp blocks (per-warp shared-memory regions)
-    "experiments_4warp": ("-DMADRL_WW_SMEM_MIN_OPL=1", "-DMADRL_HW_SPLIT=1", "-DMADRL_WW_SKIP_EMPTY_CATCH=1"),
+    "experiments_4warp": ("-DMADRL_WW_SMEM_MIN_OPL=1", "-DMADRL_HW_SPLIT=1", "-DMADRL_WW_SKIP_EMPTY_CATCH=1",
+                          "-DMADRL_PE_PHILOX_CACHE=1"),
 }
-PE_VARIANTS = ["default", "experiments"]   # the 4-warp experiment flags do not touch the Pursuit kernel
+PE_VARIANTS = sorted(VARIANTS)
 
 
 def f32(x):
