@@ -384,3 +384,107 @@ def test_hostage_reproduces_reference_golden(variant, name):
         expect[t] = g["reset_obs"][k]
     assert np.abs(obs[:, 0] - expect).max() < 1e-9
     assert eng.state(0)['counter'] == int(g["counter"])
+
+
+# ------------------------------------------------------------------ seeded random configurations
+def _ww_random_cfg(rs):
+    return dict(n_pursuers=int(rs.randint(1, 33)), n_evaders=int(rs.randint(1, 70)), n_poison=int(rs.randint(1, 70)),
+                n_sensors=int(rs.randint(1, 65)), n_coop=int(rs.randint(1, 4)), radius=float(rs.uniform(0.01, 0.06)),
+                sensor_range=float(rs.uniform(0.1, 0.45)), obstacle_radius=float(rs.uniform(0.05, 0.3)),
+                ev_speed=float(rs.uniform(0.005, 0.03)), poison_speed=float(rs.uniform(0.005, 0.03)),
+                reward_mech=['local', 'global'][rs.randint(2)], addid=bool(rs.randint(2)),
+                speed_features=bool(rs.randint(2)),
+                obstacle_loc=None if rs.randint(3) == 0 else rs.uniform(0.2, 0.8, size=2))
+
+
+@pytest.mark.parametrize("variant", ["default", "experiments"])
+@pytest.mark.parametrize("case", range(10))
+def test_waterworld_random_configurations(variant, case):
+    from emu.driver import EmuWaterworld
+    rs = np.random.RandomState(1000 + case)
+    cfg = _ww_random_cfg(rs)
+    n_obj = cfg['n_pursuers'] + cfg['n_evaders'] + cfg['n_poison']
+    E, T = 2, max(4, min(40, 1200 // n_obj))
+    seed, base = int(rs.randint(1 << 30)), int(rs.randint(1000))
+    eng = EmuWaterworld(E, seed=seed, env_id_base=base, defines=VARIANTS[variant], **cfg)
+    obs0 = eng.reset()
+    oracles = [WaterworldOracle(rng=Stream(seed, base + e), **cfg) for e in range(E)]
+    for e, o in enumerate(oracles):
+        assert np.abs(np.array(o.reset()) - obs0[e]).max() < 1e-9, (cfg, e)
+    act = rs.randn(T, E, cfg['n_pursuers'], 2) * 0.8
+    obs, rew, done, info = eng.rollout(act, auto_reset=False)
+    for t in range(T):
+        for e, o in enumerate(oracles):
+            oo, rr, dd, ii = o.step(act[t, e])
+            assert [ii['evcatches'], ii['pocatches']] == list(info[t, e]), (cfg, t, e)
+            assert np.abs(np.array(oo) - obs[t, e]).max() < 1e-9, (cfg, t, e)
+            assert np.abs(rr - rew[t, e]).max() < 1e-9, (cfg, t, e)
+    for e, o in enumerate(oracles):
+        assert eng.state(e)['counter'] == o.np_random.counter
+
+
+@pytest.mark.parametrize("variant", ["default", "experiments"])
+@pytest.mark.parametrize("case", range(10))
+def test_hostage_random_configurations(variant, case):
+    from emu.driver import EmuHostage
+    rs = np.random.RandomState(2000 + case)
+    n_good, n_host, n_bad = int(rs.randint(1, 33)), int(rs.randint(1, 50)), int(rs.randint(1, 50))
+    args = (n_good, n_host, n_bad, int(rs.randint(1, 4)), int(rs.randint(1, 3)))
+    kw = dict(radius=float(rs.uniform(0.01, 0.06)), n_sensors=int(rs.randint(1, 65)),
+              sensor_range=float(rs.uniform(0.1, 0.4)), key_radius=float(rs.uniform(0.005, 0.08)),
+              bomb_radius=float(rs.uniform(0.01, 0.08)), bad_speed=float(rs.uniform(0.005, 0.03)),
+              reward_mech=['local', 'global'][rs.randint(2)], addid=bool(rs.randint(2)))
+    if rs.randint(2):
+        kw['key_loc'] = rs.uniform(0.9, 1.0, size=(1, 2))
+    E, T = 2, max(6, min(60, 2400 // (n_good + n_host + n_bad)))
+    seed, base = int(rs.randint(1 << 30)), int(rs.randint(1000))
+    eng = EmuHostage(E, *args, seed=seed, env_id_base=base, defines=VARIANTS[variant], **kw)
+    obs0 = eng.reset()
+    oracles = [HostageOracle(*args, rng=Stream(seed, base + e), **kw) for e in range(E)]
+    for e, o in enumerate(oracles):
+        assert np.abs(np.array(o.reset()) - obs0[e]).max() < 1e-9, (args, kw, e)
+    act = rs.randn(T, E, n_good, 2) * 2.5
+    obs, rew, done, info = eng.rollout(act, auto_reset=True)
+    for t in range(T):
+        for e, o in enumerate(oracles):
+            oo, rr, dd, ii = o.step(act[t, e])
+            assert [ii['ho_saved'], ii['cr_encs']] == list(info[t, e]), (args, kw, t, e)
+            assert bool(done[t, e]) == dd and np.abs(rr - rew[t, e]).max() < 1e-9, (args, kw, t, e)
+            if dd:
+                oo = o.reset()
+            assert np.abs(np.array(oo) - obs[t, e]).max() < 1e-9, (args, kw, t, e)
+
+
+@pytest.mark.parametrize("variant", ["default", "experiments"])
+@pytest.mark.parametrize("case", range(10))
+def test_pursuit_random_configurations(variant, case):
+    from emu.driver import EmuPursuit
+    rs = np.random.RandomState(3000 + case)
+    if rs.randint(3) == 0:
+        xs, ys = int(rs.randint(2, 12)), int(rs.randint(2, 12))
+        maps = (rs.rand(int(rs.randint(1, 4)), xs, ys) < 0.15).astype(np.int32) * -1
+        maps[:, 0, 0] = 0
+    else:
+        maps = pool16()
+    cfg = dict(n_evaders=int(rs.randint(1, 65)), n_pursuers=int(rs.randint(1, 33)), obs_range=int(rs.randint(1, 12)),
+               surround=bool(rs.randint(2)), n_catch=int(rs.randint(1, 4)), flatten=bool(rs.randint(4) != 0),
+               reward_mech=['local', 'global'][rs.randint(2)], catchr=float(rs.choice([0.01, 0.1, 0.37])),
+               term_pursuit=float(rs.choice([5.0, 1.5])), urgency_reward=float(rs.choice([0.0, -0.1])),
+               include_id=bool(rs.randint(2)), sample_maps=bool(rs.randint(2)),
+               constraint_window=float(rs.choice([1.0, 0.6])), layer_norm=int(rs.choice([10, 7])))
+    E, T = 2, 25
+    seed, base = int(rs.randint(1 << 30)), int(rs.randint(1000))
+    eng = EmuPursuit(E, maps, seed=seed, env_id_base=base, defines=VARIANTS[variant], **cfg)
+    obs0 = eng.reset()
+    oracles = [PursuitOracle(maps, rng=Stream(seed, base + e), **cfg) for e in range(E)]
+    for e, o in enumerate(oracles):
+        assert np.array_equal(f32(o.reset()).reshape(obs0[e].shape), obs0[e]), (cfg, e)
+    act = rs.randint(0, 5, size=(T, E, cfg['n_pursuers'])).astype(np.int32)
+    obs, rew, done, removed = eng.rollout(act, auto_reset=False)
+    for t in range(T):
+        for e, o in enumerate(oracles):
+            oo, rr, dd, ii = o.step(act[t, e])
+            assert ii['removed'] == removed[t, e] and dd == bool(done[t, e]), (cfg, t, e)
+            assert np.array_equal(f32(oo).reshape(obs[t, e].shape), obs[t, e]), (cfg, t, e)
+            assert np.array_equal(f32(rr), rew[t, e]), (cfg, t, e)
+    check_pursuit_state(eng, oracles)
