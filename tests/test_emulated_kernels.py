@@ -488,3 +488,20 @@ def test_pursuit_random_configurations(variant, case):
             assert np.array_equal(f32(oo).reshape(obs[t, e].shape), obs[t, e]), (cfg, t, e)
             assert np.array_equal(f32(rr), rew[t, e]), (cfg, t, e)
     check_pursuit_state(eng, oracles)
+
+
+def test_integration_md_ctypes_stub_runs():
+    """The ctypes stub printed in INTEGRATION.md section 4 (config struct, create, reset_host,
+    rollout_host, destroy) is executed verbatim -- at 6 envs, against the emulator library, which
+    exports the same C ABI."""
+    import re
+    from emu import build_emu
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = re.search(r"## 4\. C ABI without PyTorch.*?```python\n(.*?)```", doc, re.S).group(1)
+    assert 'C.CDLL("madrl_b200/libmadrl_b200.so")' in code
+    code = code.replace('C.CDLL("madrl_b200/libmadrl_b200.so")', 'C.CDLL(%r)' % build_emu.build([]))
+    code = code.replace("4096", "6").replace("T = 16", "T = 4")
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    assert ns["rc"] == 0 and ns["obs"].shape == (4, 6, 5, 213)
+    assert np.isfinite(ns["obs"]).all() and ns["done"].max() <= 1 and (ns["info"] >= 0).all()
