@@ -505,3 +505,45 @@ def test_integration_md_ctypes_stub_runs():
     exec(compile(code, "INTEGRATION.md", "exec"), ns)
     assert ns["rc"] == 0 and ns["obs"].shape == (4, 6, 5, 213)
     assert np.isfinite(ns["obs"]).all() and ns["done"].max() <= 1 and (ns["info"] >= 0).all()
+
+
+def test_host_code_validation_seed_and_curriculum_knobs():
+    """Host side of the C ABI on the emulator build: argument validation never throws and reports
+    through madrl_last_error; seed() re-keys the stream and restarts the counters; Pursuit's
+    set_params (catchr, constraint_window: the curriculum knobs of pursuit_evade.py:264-272) takes
+    effect at the next step / reset."""
+    import ctypes as C
+    from emu.driver import EmuPursuit, EmuWaterworld
+    with pytest.raises(RuntimeError, match="n_pursuers"):
+        EmuWaterworld(4, 40, 5)
+    with pytest.raises(RuntimeError, match="n_sensors"):
+        EmuWaterworld(4, 5, 5, n_sensors=100)
+    eng = EmuWaterworld(3, 5, 5, seed=5)
+    lib = eng.lib
+    assert lib.madrl_ww_rollout(eng._h, 0, None, None, None, None, None, 0, None) == -1
+    assert b"T must be" in lib.madrl_last_error()
+    assert lib.madrl_ww_reset(None, None, None, None) == -1
+    with pytest.raises(RuntimeError):
+        eng.set_launch(warps_per_block=9)
+    # seed(): same seed -> same episode, different seed -> different episode
+    a = eng.reset().copy()
+    eng.seed(5)
+    assert np.array_equal(eng.reset(), a) and eng.state(0)['counter'] > 0
+    eng.seed(6)
+    assert not np.array_equal(eng.reset(), a)
+    # Pursuit curriculum knobs
+    maps = small_map()
+    cfg = dict(n_evaders=4, n_pursuers=6, obs_range=3, surround=True, reward_mech='local', catchr=0.1, term_pursuit=5.0)
+    pe = EmuPursuit(2, maps, seed=3, **cfg)
+    lib.madrl_pursuit_set_params.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    assert lib.madrl_pursuit_set_params(pe._h, 0.25, 1.0) == 0
+    pe.reset()
+    act = np.random.RandomState(0).randint(0, 5, size=(6, 2, 6)).astype(np.int32)
+    obs, rew, done, removed = pe.rollout(act, auto_reset=False)
+    oracles = [PursuitOracle(maps, rng=Stream(3, e), **dict(cfg, catchr=0.25)) for e in range(2)]
+    for o in oracles:
+        o.reset()
+    for t in range(6):
+        for e, o in enumerate(oracles):
+            oo, rr, dd, ii = o.step(act[t, e])
+            assert np.array_equal(f32(rr), rew[t, e]) and ii['removed'] == removed[t, e]
