@@ -128,6 +128,14 @@ __device__ __noinline__ Spawn<real> spawn_object(uint64_t seed, uint32_t env_id,
 #ifndef MADRL_WW_ONE_WARP_BLOCKS
 #define MADRL_WW_ONE_WARP_BLOCKS MADRL_ONE_WARP_BLOCKS   // see common.cuh
 #endif
+#ifndef MADRL_WW_LEAN_SENSE
+// 1 (experiment, shuffle-scan path): (a) which pursuers have the obstacle within sensing range is
+// one ballot per step (from the distances the rebound test computes anyway) instead of a per-pursuer
+// distance computation; (b) a class without any in-range candidate for this pursuer -- the common
+// case: ~0.6 evaders, ~1.3 poisons, ~0.5 other pursuers are in range on average in C2 -- skips its
+// velocity shuffles, found-tests and feature arithmetic and stores zeros directly.
+#define MADRL_WW_LEAN_SENSE 0
+#endif
 #ifndef MADRL_WW_SKIP_EMPTY_CATCH
 #define MADRL_WW_SKIP_EMPTY_CATCH 0   // 1 (experiment): skip catches / respawn / mask reductions on steps without any collision
 #endif
@@ -293,13 +301,22 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
           pen = p.control_penalty * (p.reward_global ? warp_sum(sq) : sq);
         }
         // ---- obstacle rebound (velocity only): ww:247-270 ----------------------------------------
+#if MADRL_WW_LEAN_SENSE
+        unsigned obst_mask = 0u;   // pursuers with the obstacle inside the conservative sensing range
+#endif
 #pragma unroll
         for (int c = 0; c < OPL; ++c) {
           const bool oE = (mE[c] >> lane) & 1u, oP = (mP[c] >> lane) & 1u, oU = (mU[c] >> lane) & 1u;
           const real thr = oU ? p.obst2_p : (oE ? p.obst2_e : (oP ? p.obst2_po : (real)-1));
           const real kf = oP ? (real)-1 : (real)-0.5;                  // ww:254,262,270
           const real dx = x[c] - obx, dy = y[c] - oby;
+#if MADRL_WW_LEAN_SENSE
+          const real do2 = dx * dx + dy * dy;
+          if (c == 0) obst_mask = __ballot_sync(FULL_MASK, lane < p.Np && do2 <= p.cull2);
+          if (do2 <= thr) { vx[c] = kf * vx[c]; vy[c] = kf * vy[c]; }
+#else
           if (dx * dx + dy * dy <= thr) { vx[c] = kf * vx[c]; vy[c] = kf * vy[c]; }
+#endif
         }
         // ---- sense: one pursuer at a time -----------------------------------------------------
         real* obs_row = obs_t;
@@ -315,7 +332,11 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
           for (int kc = 0; kc < KCH; ++kc) {
             bO[kc] = bE[kc] = bP[kc] = bU[kc] = INF;
             iE[kc] = iP[kc] = iU[kc] = 0;
+#if MADRL_WW_LEAN_SENSE
+            if ((obst_mask >> pi) & 1u) {   // warp-uniform; the exact tests below decide
+#else
             if (od2 <= p.cull2) {   // the obstacle is sensed like a point object (pursuer radius only)
+#endif
               const real sv = sx_l[kc] * orx + sy_l[kc] * ory;
               const bool ok = !((sv < (real)0) | (sv > p.range) | (od2 - sv * sv > p.r_p2));
               bO[kc] = ok ? sv : INF;
@@ -402,6 +423,9 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
             }
             __syncwarp();   // the next pursuer's staging overwrites the slots
           } else {
+#if MADRL_WW_LEAN_SENSE
+          unsigned candU = 0u, candE = 0u, candP = 0u;   // warp-uniform: in-range candidates per class
+#endif
 #pragma unroll
           for (int c = 0; c < OPL; ++c) {
             // lanes as OBJECTS: geometry, collisions (ww:278-293), conservative range cull
@@ -409,6 +433,9 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
             const real d2 = rx * rx + ry * ry;
             unsigned cm = __ballot_sync(FULL_MASK, d2 <= cull2_l[c]);
             if (c == 0) cm &= ~(1u << pi);  // ww:70-71 `same`
+#if MADRL_WW_LEAN_SENSE
+            candU |= cm & mU[c]; candE |= cm & mE[c]; candP |= cm & mP[c];
+#endif
             const bool hit = d2 <= coll2_l[c];
             if (hit) col[c] |= 1u << pi;
 #if !MADRL_WW_DEFERRED_TAIL
@@ -458,6 +485,44 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
             }
 #endif
           }
+#if MADRL_WW_LEAN_SENSE
+#pragma unroll
+          for (int kc = 0; kc < KCH; ++kc) {
+            const real sx = sx_l[kc], sy = sy_l[kc];
+            // features ww:312-353, 388-395: feature-major, sensor-minor
+            const int k = lane + 32 * kc;
+            const real z = (real)0;
+            real* o = obs_row + 32 * kc;   // this lane's column
+            real fE = z, sE = z, fP = z, sP = z, fU = z, sU = z;
+#define MADRL_WW_CLASS(CAND, BEST, IDX, F, S)                                                     \
+  if ((CAND) != 0u) {                                                                              \
+    const bool h = BEST[kc] < INF;                                                                 \
+    F = h ? BEST[kc] : z;                                                                          \
+    if (p.speed_features) {                                                                        \
+      real ox = z, oy = z;                                                                         \
+      _Pragma("unroll") for (int c = 0; c < OPL; ++c) {                                            \
+        const real cx_ = __shfl_sync(FULL_MASK, vx[c], IDX[kc] & 31), cy_ = __shfl_sync(FULL_MASK, vy[c], IDX[kc] & 31); \
+        if (OPL == 1 || (IDX[kc] >> 5) == c) { ox = cx_; oy = cy_; }                               \
+      }                                                                                            \
+      S = h ? sx * (ox - mvx) + sy * (oy - mvy) : z;                                               \
+    }                                                                                              \
+  }
+            MADRL_WW_CLASS(candE, bE, iE, fE, sE)
+            MADRL_WW_CLASS(candP, bP, iP, fP, sP)
+            MADRL_WW_CLASS(candU, bU, iU, fU, sU)
+#undef MADRL_WW_CLASS
+            if (k < K) {
+              store_stream(o + 0 * K, bO[kc] < INF ? bO[kc] : z);
+              if (p.speed_features) {
+                store_stream(o + 1 * K, fE); store_stream(o + 2 * K, sE);
+                store_stream(o + 3 * K, fP); store_stream(o + 4 * K, sP);
+                store_stream(o + 5 * K, fU); store_stream(o + 6 * K, sU);
+              } else {
+                store_stream(o + 1 * K, fE); store_stream(o + 2 * K, fP); store_stream(o + 3 * K, fU);
+              }
+            }
+          }
+#else
 #pragma unroll
           for (int kc = 0; kc < KCH; ++kc) {
             const real sx = sx_l[kc], sy = sy_l[kc];
@@ -500,6 +565,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
               store_stream(o + 3 * K, hU ? bU[kc] : z);
             }
           }
+#endif
           }
 #if !MADRL_WW_DEFERRED_TAIL
           // ww:411-428 tail: collided-with-evader, collided-with-poison, id -- one branch-free store
