@@ -66,6 +66,12 @@ __device__ __forceinline__ real unit_at(uint64_t seed, uint32_t env_id, uint64_t
 // the reward logic computes anyway, instead of a ballot + a 6-lane store per rescuer.
 #define MADRL_HW_DEFERRED_TAIL 1
 #endif
+#ifndef MADRL_HW_LEAN_SENSE
+// 1 (experiment): which rescuers have the key / the bomb within sensing range is two ballots per
+// step (from the distances the collision test computes anyway) instead of per-rescuer arithmetic; a
+// rescuer with no criminal in range skips the velocity shuffles and the feature arithmetic.
+#define MADRL_HW_LEAN_SENSE 0
+#endif
 #ifndef MADRL_HW_SPLIT
 // 1 (experiment): the rescuers live in their own four registers (lane i = rescuer i) and the
 // per-lane object registers hold only what is sensed and collided with -- criminals, then hostages.
@@ -252,10 +258,21 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
         // ---- key / bomb collisions of every rescuer up front (the obs tail needs the post-step
         //      gate flag): hw:286-296 ----------------------------------------------------------------
         unsigned coll_ke, coll_bo;
+#if MADRL_HW_LEAN_SENSE
+        unsigned key_near, bomb_near;
+#endif
         {
           const real dkx = rpx - kx, dky = rpy - ky, dbx = rpx - bx, dby = rpy - by;
+#if MADRL_HW_LEAN_SENSE
+          const real dk2 = dkx * dkx + dky * dky, db2 = dbx * dbx + dby * dby;
+          coll_ke = __ballot_sync(FULL_MASK, lane < p.Nr && dk2 <= p.coll2_key);
+          coll_bo = __ballot_sync(FULL_MASK, lane < p.Nr && db2 <= p.coll2_bomb);
+          key_near = __ballot_sync(FULL_MASK, lane < p.Nr && dk2 <= p.cull2);    // conservative range cull;
+          bomb_near = __ballot_sync(FULL_MASK, lane < p.Nr && db2 <= p.cull2);   // the exact tests decide
+#else
           coll_ke = __ballot_sync(FULL_MASK, lane < p.Nr && dkx * dkx + dky * dky <= p.coll2_key);
           coll_bo = __ballot_sync(FULL_MASK, lane < p.Nr && dbx * dbx + dby * dby <= p.coll2_bomb);
+#endif
         }
         const bool gate_post = gate_pre || (coll_ke != 0u);
         // ---- sense: one rescuer at a time -----------------------------------------------------------
@@ -272,12 +289,20 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
             bK[kc] = bB[kc] = bC[kc] = bH[kc] = INF;
             iC[kc] = 0;
             const real sx = sx_l[kc], sy = sy_l[kc];
+#if MADRL_HW_LEAN_SENSE
+            if (!gate_pre && ((key_near >> pi) & 1u)) {                           // hw:343-345
+#else
             if (!gate_pre && kd2 <= p.cull2) {                                    // hw:343-345
+#endif
               const real sv = sx * krx + sy * kry;
               const bool ok = !((sv < (real)0) | (sv > p.range) | (kd2 - sv * sv > p.r_r2));
               bK[kc] = ok ? sv : INF;
             }
+#if MADRL_HW_LEAN_SENSE
+            if ((bomb_near >> pi) & 1u) {
+#else
             if (bd2 <= p.cull2) {
+#endif
               const real sv = sx * brx + sy * bry;
               const bool ok = !((sv < (real)0) | (sv > p.range) | (bd2 - sv * sv > p.r_r2));
               bB[kc] = ok ? sv : INF;
@@ -286,12 +311,18 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
 #if !MADRL_HW_DEFERRED_TAIL
           unsigned hitC = 0u, hitH = 0u;
 #endif
+#if MADRL_HW_LEAN_SENSE
+          unsigned candC = 0u;   // warp-uniform: criminals within range of this rescuer
+#endif
 #pragma unroll
           for (int c = 0; c < OPL; ++c) {
             const real rx = x[c] - mx, ry = y[c] - my;
             const real d2 = rx * rx + ry * ry;
             // saved hostages are invisible (pre-step mask, hw:301) but still collide (hw:269-275)
             const unsigned cm = __ballot_sync(FULL_MASK, d2 <= cull2_l[c] && !sav[c]);
+#if MADRL_HW_LEAN_SENSE
+            candC |= cm & mC[c];
+#endif
             const bool hit = d2 <= coll2_l[c];
             if (hit) col[c] |= 1u << pi;
 #if !MADRL_HW_DEFERRED_TAIL
@@ -328,6 +359,24 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
             // features hw:395-397: [criminal dist, criminal speed, hostage dist, key dist, bomb dist]
             const int k = lane + 32 * kc;
             const real z = (real)0;
+#if MADRL_HW_LEAN_SENSE
+            real fC = z, sC = z;
+            if (candC != 0u) {
+              real oCx = z, oCy = z;
+#pragma unroll
+              for (int c = 0; c < OPL; ++c) {
+                const real cx_ = __shfl_sync(FULL_MASK, vx[c], iC[kc] & 31), cy_ = __shfl_sync(FULL_MASK, vy[c], iC[kc] & 31);
+                if (OPL == 1 || (iC[kc] >> 5) == c) { oCx = cx_; oCy = cy_; }
+              }
+              const bool hC = bC[kc] < INF;
+              fC = hC ? bC[kc] : z;
+              sC = hC ? sx * (oCx - mvx) + sy * (oCy - mvy) : z;
+            }
+            if (k < K) {
+              real* o = obs_row + 32 * kc;
+              store_stream(o + 0 * K, fC);
+              store_stream(o + 1 * K, sC);
+#else
             real oCx, oCy;
             if (OPL == 1) {
               oCx = __shfl_sync(FULL_MASK, vx[0], iC[kc]); oCy = __shfl_sync(FULL_MASK, vy[0], iC[kc]);
@@ -344,6 +393,7 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
               const bool hC = bC[kc] < INF;
               store_stream(o + 0 * K, hC ? bC[kc] : z);
               store_stream(o + 1 * K, hC ? sx * (oCx - mvx) + sy * (oCy - mvy) : z);
+#endif
               store_stream(o + 2 * K, bH[kc] < INF ? bH[kc] : z);
               store_stream(o + 3 * K, bK[kc] < INF ? bK[kc] : z);
               store_stream(o + 4 * K, bB[kc] < INF ? bB[kc] : z);

@@ -24,10 +24,11 @@ VARIANTS = {
     # what scripts/build_variants.sh builds as `all`: one-warp blocks, shared-memory candidate staging
     # for >= 2 objects per lane, lean shuffle path otherwise, split Hostage layout, ...
     "experiments": ("-DMADRL_ONE_WARP_BLOCKS=1", "-DMADRL_WW_SMEM_MIN_OPL=2", "-DMADRL_WW_LEAN_SENSE=1",
-                    "-DMADRL_HW_SPLIT=1", "-DMADRL_WW_SKIP_EMPTY_CATCH=1", "-DMADRL_PE_PHILOX_CACHE=1"),
+                    "-DMADRL_HW_SPLIT=1", "-DMADRL_HW_LEAN_SENSE=1", "-DMADRL_WW_SKIP_EMPTY_CATCH=1",
+                    "-DMADRL_PE_PHILOX_CACHE=1"),
     # the same flags on the default 4-warp blocks (per-warp shared-memory regions), with the lean
     # shuffle path up to 2 objects per lane and the staging from 4
-    "experiments_4warp": ("-DMADRL_WW_SMEM_MIN_OPL=4", "-DMADRL_WW_LEAN_SENSE=1", "-DMADRL_HW_SPLIT=1",
+    "experiments_4warp": ("-DMADRL_WW_SMEM_MIN_OPL=4", "-DMADRL_WW_LEAN_SENSE=1", "-DMADRL_HW_LEAN_SENSE=1",
                           "-DMADRL_WW_SKIP_EMPTY_CATCH=1", "-DMADRL_PE_PHILOX_CACHE=1"),
 }
 PE_VARIANTS = sorted(VARIANTS)
