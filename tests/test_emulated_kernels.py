@@ -551,3 +551,37 @@ def test_host_code_validation_seed_and_curriculum_knobs():
         for e, o in enumerate(oracles):
             oo, rr, dd, ii = o.step(act[t, e])
             assert np.array_equal(f32(rr), rew[t, e]) and ii['removed'] == removed[t, e]
+
+
+@pytest.mark.parametrize("family", ["waterworld", "hostage"])
+def test_timestep_limit_horizon_with_auto_reset(family):
+    """The env's own 1000-step horizon (waterworld.py:124-126, hostage.py:181-184) followed by the
+    in-place reset, one env, 1 010 steps."""
+    from emu.driver import EmuHostage, EmuWaterworld
+    T, seed = 1010, 21
+    rs = np.random.RandomState(4)
+    if family == "waterworld":
+        cfg = dict(n_pursuers=2, n_evaders=3, n_poison=2, n_sensors=5)
+        eng = EmuWaterworld(1, seed=seed, **cfg)
+        orc = WaterworldOracle(rng=Stream(seed, 0), **cfg)
+        act = rs.randn(T, 1, 2, 2) * 0.3
+    else:
+        args = (2, 3, 2, 3, 1)
+        kw = dict(n_sensors=5, bomb_radius=1e-4)    # a bomb nobody hits and hostages nobody can all save
+        eng = EmuHostage(1, *args, seed=seed, **kw)
+        orc = HostageOracle(*args, rng=Stream(seed, 0), **kw)
+        act = rs.randn(T, 1, 2, 2) * 0.3
+    assert np.abs(np.array(orc.reset()) - eng.reset()[0]).max() < 1e-9
+    obs, rew, done, info = eng.rollout(act, auto_reset=True)
+    n_done = 0
+    for t in range(T):
+        oo, rr, dd, ii = orc.step(act[t, 0])
+        assert bool(done[t, 0]) == dd, t
+        assert np.abs(rr - rew[t, 0]).max() < 1e-9, t
+        if dd:
+            oo = orc.reset()
+            n_done += 1
+        assert np.abs(np.array(oo) - obs[t, 0]).max() < 1e-9, t
+    assert n_done >= 1
+    if family == "waterworld":
+        assert bool(done[998, 0]) and done.sum() == 1   # reset() consumed step 1: index 998 is the 1000th step
