@@ -585,3 +585,33 @@ def test_timestep_limit_horizon_with_auto_reset(family):
     assert n_done >= 1
     if family == "waterworld":
         assert bool(done[998, 0]) and done.sum() == 1   # reset() consumed step 1: index 998 is the 1000th step
+
+
+@pytest.mark.parametrize("variant", ["default", "experiments"])
+def test_waterworld_fused_peer_gather_layout(variant):
+    """The PEER instantiation of the Waterworld kernel (in-kernel stores into other ranks' gather
+    buffers over NVLink, madrl_ww_set_peers): two "ranks" with different env shards write their
+    reward / done / info rows into slot `rank` of two destination buffers, env-major
+    [n_slots][E][t_max][...], including partial reward runs at the end of the rollout."""
+    import ctypes as C
+    from emu.driver import EmuWaterworld
+    cfg = dict(n_pursuers=5, n_evaders=5)
+    E, T, t_max, n_ranks = 3, 37, 40, 2     # 37 steps: a partial 32-step done/info flush and reward run
+    dests = [dict(rew=np.full((n_ranks, E, t_max, 5), np.nan), done=np.full((n_ranks, E, t_max), 255, np.uint8),
+                  info=np.full((n_ranks, E, t_max, 2), -1, np.int32)) for _ in range(2)]
+    outs = []
+    for rank in range(n_ranks):
+        eng = EmuWaterworld(E, seed=8, env_id_base=rank * E, max_path_length=9, defines=VARIANTS[variant], **cfg)
+        arr = lambda k: (C.c_void_p * 2)(*[d[k].ctypes.data for d in dests])   # noqa: E731
+        eng.lib.madrl_ww_set_peers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                               C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        assert eng.lib.madrl_ww_set_peers(eng._h, 2, rank, t_max, arr('rew'), arr('done'), arr('info')) == 0
+        eng.reset()
+        act = np.random.RandomState(rank).randn(T, E, 5, 2) * 0.5
+        outs.append(eng.rollout(act, auto_reset=True))
+    for d in dests:
+        for rank, (obs, rew, done, info) in enumerate(outs):
+            assert np.array_equal(d['rew'][rank, :, :T], rew.transpose(1, 0, 2))
+            assert np.array_equal(d['done'][rank, :, :T], done.T)
+            assert np.array_equal(d['info'][rank, :, :T], info.transpose(1, 0, 2))
+            assert np.isnan(d['rew'][rank, :, T:]).all() and (d['done'][rank, :, T:] == 255).all()
