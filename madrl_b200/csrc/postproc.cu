@@ -143,7 +143,10 @@ __global__ void episode_stats_kernel(int T, int E, int A, const float* __restric
 // order by one warp (no atomics), so a given input always yields the same bits.
 //
 // Three series are derived per element from (a, b):  s0 = a,  s1 = b,  s2 = b - a  (b optional).
-constexpr int kMomBlocks = 592;          // 4 CTAs x 148 SMs
+#ifndef MADRL_MOM_BLOCKS
+#define MADRL_MOM_BLOCKS 592           // 4 CTAs x 148 SMs (the CPU emulator of tests/emu builds with fewer)
+#endif
+constexpr int kMomBlocks = MADRL_MOM_BLOCKS;
 constexpr int kMomThreads = 256;
 constexpr int kMomSeries = 3;
 static_assert(kMomBlocks * 2 * kMomSeries <= MADRL_MOMENTS_WS, "workspace too small");
@@ -252,7 +255,7 @@ extern "C" int madrl_episode_stats_f32(int T, int E, int A, const float* rew_dev
   MADRL_REQUIRE(T >= 1 && E >= 1 && A >= 1 && max_traj_len >= 1, "bad sizes");
   MADRL_REQUIRE(rew_dev && done_dev && carry_dev && ep_reward_dev && ep_disc_dev && ep_len_dev && ep_end_dev,
                 "NULL buffer");
-  episode_stats_kernel<<<(unsigned)((E + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+  MADRL_LAUNCH(episode_stats_kernel, (unsigned)((E + 127) / 128), 128, 0, (cudaStream_t)stream, 
       T, E, A, rew_dev, done_dev, discount, max_traj_len, carry_dev, ep_reward_dev, ep_disc_dev, ep_len_dev,
       ep_end_dev);
   g_launches.fetch_add(1);
@@ -266,7 +269,7 @@ extern "C" int madrl_gae_f32(int T, int E, int A, const float* rew_dev, const fl
   MADRL_REQUIRE(T >= 1 && E >= 1 && A >= 1, "bad sizes");
   MADRL_REQUIRE(rew_dev && value_dev && done_dev && adv_dev && ret_dev, "NULL buffer");
   const size_t n = (size_t)E * A;
-  gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  MADRL_LAUNCH(gae_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, 
       T, E, A, rew_dev, value_dev, done_dev, last_value_dev, discount, gae_lambda, adv_dev, ret_dev);
   g_launches.fetch_add(1);
   MADRL_CUDA_CHECK(cudaGetLastError());
@@ -282,7 +285,7 @@ extern "C" int madrl_frame_stack_f32(int T, int E, int A, int D, int B, const fl
   const size_t n = (size_t)E * A * D;
   const unsigned grid = (unsigned)((n + 255) / 256);
   cudaStream_t s = (cudaStream_t)stream;
-#define MADRL_FS(BB) case BB: frame_stack_kernel<BB><<<grid, 256, 0, s>>>(T, n, A * D, obs_dev, done_dev, E, carry_dev, out_dev); break
+#define MADRL_FS(BB) case BB: MADRL_LAUNCH(frame_stack_kernel<BB>, grid, 256, 0, s, T, n, A * D, obs_dev, done_dev, E, carry_dev, out_dev); break
   switch (B) { MADRL_FS(1); MADRL_FS(2); MADRL_FS(3); MADRL_FS(4); MADRL_FS(5); MADRL_FS(6); MADRL_FS(7); MADRL_FS(8); }
 #undef MADRL_FS
   g_launches.fetch_add(1);
@@ -295,7 +298,7 @@ extern "C" int madrl_standardize_f32(int T, size_t n, float* x_dev, double* mean
                                      void* stream) {
   MADRL_REQUIRE(T >= 1 && n >= 1, "bad sizes");
   MADRL_REQUIRE(x_dev && mean_dev && var_dev, "NULL buffer");
-  standardize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  MADRL_LAUNCH(standardize_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, 
       T, n, x_dev, mean_dev, var_dev, alpha, eps, center, scale, enable);
   g_launches.fetch_add(1);
   MADRL_CUDA_CHECK(cudaGetLastError());
@@ -303,10 +306,10 @@ extern "C" int madrl_standardize_f32(int T, size_t n, float* x_dev, double* mean
 }
 
 static int run_moments(size_t n, const float* a, const float* b, double* stats, double* ws, cudaStream_t s) {
-  moments_partial_kernel<<<kMomBlocks, kMomThreads, 0, s>>>(n, a, b, nullptr, ws);
-  moments_finalize_kernel<<<1, 32, 0, s>>>(n, ws, 0, stats);
-  moments_partial_kernel<<<kMomBlocks, kMomThreads, 0, s>>>(n, a, b, stats, ws);
-  moments_finalize_kernel<<<1, 32, 0, s>>>(n, ws, 1, stats);
+  MADRL_LAUNCH(moments_partial_kernel, kMomBlocks, kMomThreads, 0, s, n, a, b, nullptr, ws);
+  MADRL_LAUNCH(moments_finalize_kernel, 1, 32, 0, s, n, ws, 0, stats);
+  MADRL_LAUNCH(moments_partial_kernel, kMomBlocks, kMomThreads, 0, s, n, a, b, stats, ws);
+  MADRL_LAUNCH(moments_finalize_kernel, 1, 32, 0, s, n, ws, 1, stats);
   g_launches.fetch_add(4);
   MADRL_CUDA_CHECK(cudaGetLastError());
   return MADRL_OK;
@@ -320,7 +323,7 @@ extern "C" int madrl_center_advantages_f32(size_t n, float* adv_dev, int center,
   const int rc = run_moments(n, adv_dev, nullptr, stats_dev, workspace_dev, s);
   if (rc) return rc;
   if (center || positive) {
-    center_apply_kernel<<<kMomBlocks, kMomThreads, 0, s>>>(n, adv_dev, stats_dev, center, positive);
+    MADRL_LAUNCH(center_apply_kernel, kMomBlocks, kMomThreads, 0, s, n, adv_dev, stats_dev, center, positive);
     g_launches.fetch_add(1);
     MADRL_CUDA_CHECK(cudaGetLastError());
   }

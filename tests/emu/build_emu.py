@@ -11,7 +11,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "madrl_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-SOURCES = ["common.cu", "waterworld.cu", "pursuit.cu", "hostage.cu"]   # postproc.cu: multi-warp blocks with static smem, GPU-only
+SOURCES = ["common.cu", "waterworld.cu", "pursuit.cu", "hostage.cu", "postproc.cu"]
+# postproc.cu: its shared arrays are block-static, not `extern`; the fixed reduction grid (592 blocks of
+# 256 threads on the GPU) is narrowed so that a launch does not create 150 000 fibers
+PER_FILE_FLAGS = {"postproc.cu": ["-D__shared__=static", "-DMADRL_MOM_BLOCKS=6"]}
 CXXFLAGS = ["-std=c++17", "-O1", "-g", "-fPIC", "-Wno-unknown-pragmas", "-Wno-attributes", "-x", "c++",
             "-I", os.path.join(HERE, "include")]
 
@@ -35,7 +38,7 @@ def build(defines=(), force=False):
 
     def one(src):
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
-        cmd = [cxx] + CXXFLAGS + list(defines) + ["-c", "-o", obj, src]
+        cmd = [cxx] + CXXFLAGS + list(defines) + PER_FILE_FLAGS.get(os.path.basename(src), []) + ["-c", "-o", obj, src]
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if res.returncode:
             sys.stderr.write(res.stdout)
@@ -43,7 +46,7 @@ def build(defines=(), force=False):
         return obj
 
     srcs = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(HERE, "emu_runtime.cpp")]
-    with ThreadPoolExecutor(max_workers=5) as pool:
+    with ThreadPoolExecutor(max_workers=6) as pool:
         objs = list(pool.map(one, srcs))
     subprocess.check_call([cxx, "-shared", "-o", lib] + objs)
     return lib

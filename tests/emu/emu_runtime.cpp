@@ -164,11 +164,13 @@ void run_grid(unsigned grid, unsigned block, size_t smem, const std::function<vo
   g_body = &body;
   gridDim = dim3(grid);
   blockDim = dim3(block);
+  std::vector<char*> stacks(block);   // fiber stacks, reused by every block of the grid
+  for (auto& st : stacks) st = static_cast<char*>(malloc(kStackBytes));
   for (unsigned b = 0; b < grid; ++b) {
     blockIdx = uint3{b, 0, 0};
     // uninitialised shared memory must not be relied upon: poison it
-    memset(madrl::ww_smem, 0xCD, madrl::kEmuSmemBytes);
-    memset(madrl::smem_u32, 0xCD, madrl::kEmuSmemBytes);
+    memset(madrl::ww_smem, 0xCD, smem);      // only what the launch asked for is addressable
+    memset(madrl::smem_u32, 0xCD, smem);
     g_shadow.clear();
     g_fibers.assign(block, Fiber());
     g_warps.assign(block / 32, Rendezvous());
@@ -176,7 +178,7 @@ void run_grid(unsigned grid, unsigned block, size_t smem, const std::function<vo
     for (unsigned t = 0; t < block; ++t) {
       Fiber& f = g_fibers[t];
       f.tid = t;
-      f.stack = static_cast<char*>(malloc(kStackBytes));
+      f.stack = stacks[t];
       getcontext(&f.ctx);
       f.ctx.uc_stack.ss_sp = f.stack;
       f.ctx.uc_stack.ss_size = kStackBytes;
@@ -209,8 +211,8 @@ void run_grid(unsigned grid, unsigned block, size_t smem, const std::function<vo
         seen = g_progress;
       }
     }
-    for (auto& f : g_fibers) free(f.stack);
   }
+  for (char* st : stacks) free(st);
   g_fibers.clear();
   g_cur = -1;
   g_body = nullptr;

@@ -30,7 +30,9 @@
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __grid_constant__
+#ifndef __shared__   // postproc.cu is compiled with -D__shared__=static (block-static arrays; blocks run one at a time)
 #define __shared__
+#endif
 #define __align__(n) __attribute__((aligned(n)))
 
 // ---- vector types -----------------------------------------------------------------------------
