@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE -- not part of the product.
 //
-// A stand-in for <cuda_runtime.h> that lets g++ compile madrl_b200/csrc/{waterworld,pursuit,hostage,
+// A stand-in for <cuda_runtime.h> that lets g++ compile madrl_b200/csrc/{waterworld,pursuit,hostage,postproc,
 // common}.cu unchanged, so that the `-m "not gpu"` test suite can execute the KERNEL SOURCE on the
 // CPU and compare it with the oracle (tests/test_emulated_kernels.py).  Every CUDA thread of a block
 // runs as a fiber (ucontext) on one OS thread; warp collectives (__shfl_sync, __ballot_sync,
