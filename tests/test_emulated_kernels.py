@@ -615,3 +615,59 @@ def test_waterworld_fused_peer_gather_layout(variant):
             assert np.array_equal(d['done'][rank, :, :T], done.T)
             assert np.array_equal(d['info'][rank, :, :T], info.transpose(1, 0, 2))
             assert np.isnan(d['rew'][rank, :, T:]).all() and (d['done'][rank, :, T:] == 255).all()
+
+
+def _vec_executor_check(eng, oracles, act, mpl, exact, info_of):
+    """VecEnvExecutor.step semantics (vec_env_executor.py:16-28) against per-env oracles: done at the
+    env's own terminal state or at max_path_length, reset in place, obs slot = reset observation."""
+    T, E = act.shape[:2]
+    obs, rew, done, info = eng.rollout(act, auto_reset=True)
+    ts = np.zeros(E, int)
+    for t in range(T):
+        for e, o in enumerate(oracles):
+            oo, rr, dd, ii = o.step(act[t, e])
+            ts[e] += 1
+            dd = dd or ts[e] >= mpl
+            assert bool(done[t, e]) == dd, (t, e)
+            assert info_of(ii) == list(np.atleast_1d(info[t, e])), (t, e)
+            if dd:
+                oo = o.reset()
+                ts[e] = 0
+            if exact:
+                assert np.array_equal(f32(oo).reshape(obs[t, e].shape), obs[t, e]) and np.array_equal(f32(rr), rew[t, e])
+            else:
+                assert np.abs(np.array(oo) - obs[t, e]).max() < 1e-9 and np.abs(rr - rew[t, e]).max() < 1e-9, (t, e)
+
+
+@pytest.mark.parametrize("variant", ["default", "experiments"])
+@pytest.mark.parametrize("case", range(5))
+def test_random_configurations_with_horizon_and_auto_reset(variant, case):
+    from emu.driver import EmuHostage, EmuPursuit, EmuWaterworld
+    rs = np.random.RandomState(7000 + case)
+    mpl, seed, base, E, T = int(rs.randint(3, 12)), int(rs.randint(1 << 30)), int(rs.randint(1000)), 3, 30
+    # Waterworld
+    cfg = _ww_random_cfg(rs)
+    cfg.update(n_evaders=min(cfg['n_evaders'], 20), n_poison=min(cfg['n_poison'], 20))
+    eng = EmuWaterworld(E, seed=seed, env_id_base=base, max_path_length=mpl, defines=VARIANTS[variant], **cfg)
+    orc = [WaterworldOracle(rng=Stream(seed, base + e), **cfg) for e in range(E)]
+    eng.reset(); [o.reset() for o in orc]
+    _vec_executor_check(eng, orc, rs.randn(T, E, cfg['n_pursuers'], 2) * 0.8, mpl, False,
+                        lambda ii: [ii['evcatches'], ii['pocatches']])
+    # Hostage
+    args = (int(rs.randint(1, 12)), int(rs.randint(1, 20)), int(rs.randint(1, 20)), int(rs.randint(1, 3)), 1)
+    kw = dict(radius=float(rs.uniform(0.02, 0.06)), n_sensors=int(rs.randint(1, 40)), key_radius=0.05,
+              reward_mech=['local', 'global'][rs.randint(2)])
+    eng = EmuHostage(E, *args, seed=seed, env_id_base=base, max_path_length=mpl, defines=VARIANTS[variant], **kw)
+    orc = [HostageOracle(*args, rng=Stream(seed, base + e), **kw) for e in range(E)]
+    eng.reset(); [o.reset() for o in orc]
+    _vec_executor_check(eng, orc, rs.randn(T, E, args[0], 2) * 2.0, mpl, False, lambda ii: [ii['ho_saved'], ii['cr_encs']])
+    # Pursuit
+    pcfg = dict(n_evaders=int(rs.randint(1, 12)), n_pursuers=int(rs.randint(1, 12)), obs_range=int(rs.randint(1, 8)),
+                surround=bool(rs.randint(2)), n_catch=int(rs.randint(1, 3)), reward_mech=['local', 'global'][rs.randint(2)],
+                catchr=0.1, sample_maps=True, flatten=bool(rs.randint(2)))
+    maps = pool16() if rs.randint(2) else small_map()
+    eng = EmuPursuit(E, maps, seed=seed, env_id_base=base, max_path_length=mpl, defines=VARIANTS[variant], **pcfg)
+    orc = [PursuitOracle(maps, rng=Stream(seed, base + e), **pcfg) for e in range(E)]
+    eng.reset(); [o.reset() for o in orc]
+    _vec_executor_check(eng, orc, rs.randint(0, 5, size=(T, E, pcfg['n_pursuers'])).astype(np.int32), mpl, True,
+                        lambda ii: [ii['removed']])
