@@ -671,3 +671,23 @@ def test_random_configurations_with_horizon_and_auto_reset(variant, case):
     eng.reset(); [o.reset() for o in orc]
     _vec_executor_check(eng, orc, rs.randint(0, 5, size=(T, E, pcfg['n_pursuers'])).astype(np.int32), mpl, True,
                         lambda ii: [ii['removed']])
+
+
+def test_host_entry_points_equal_device_entry_points():
+    """*_reset_host / *_rollout_host (staging copies inside the library) against the device-pointer
+    entry points, Pursuit and Hostage (Waterworld: see the auto-reset test above)."""
+    import ctypes as C
+    from emu.driver import EmuHostage, EmuPursuit, Guarded, _p
+    maps = pool16()
+    mk = [lambda: EmuPursuit(4, maps, seed=3, max_path_length=6, **C3),
+          lambda: EmuHostage(4, 10, 16, 16, 4, 2, seed=3, max_path_length=6, fp64=False)]
+    acts = [np.random.RandomState(0).randint(0, 5, size=(14, 4, 8)).astype(np.int32),
+            np.random.RandomState(1).randn(14, 4, 10, 2).astype(np.float32)]
+    for make, act in zip(mk, acts):
+        a, b = make(), make()
+        oa = a.reset()
+        ob = Guarded(oa.shape, oa.dtype, 0)
+        assert b._f("reset_host")(b._h, None, _p(ob.arr)) == 0
+        assert np.array_equal(oa, ob.check("obs"))
+        for x, y in zip(a.rollout(act, host=False), b.rollout(act, host=True)):
+            assert np.array_equal(x, y)
