@@ -193,50 +193,3 @@ class HostageOracle(object):
         self.gate_open, self.bombed, self.t = bool(s['gate_open']), bool(s['bombed']), int(s['t'])
         if 'counter' in s and hasattr(self.np_random, 'counter'):
             self.np_random.counter = int(s['counter'])
-
-
-def fragile_step(o, state, action, eps):
-    """True if a comparison of the step from `state` is within `eps` of its threshold (test helper;
-    same idea as waterworld_oracle.fragile_step)."""
-    def near(a, b):
-        d = np.abs(np.asarray(a, dtype=np.float64) - b)
-        return bool(np.any((d < eps) & (d > 0)))
-
-    rx = np.asarray(state['rx'], float); rv = np.asarray(state['rv'], float)
-    hx = np.asarray(state['hx'], float); cx = np.asarray(state['cx'], float)
-    cv = np.asarray(state['cv'], float)
-    bomb = np.asarray(state['bomb'], float).reshape(1, 2)
-    key = np.asarray(state['key'], float).reshape(1, 2)
-    act = np.asarray(action, float).reshape(o.Nr, 2) * o.action_scale
-    rv = rv + act
-    rx = rx + rv
-    if near(rx, 0.0) or near(rx, 1.0):
-        return True
-    rx = np.clip(rx, 0, 1)
-    if not state['gate_open']:
-        if near(rx, 0.5 + o.radius):
-            return True
-        rx = np.clip(rx, 0.5 + o.radius, 1)
-    if near(ssd.cdist(rx, hx), o.r_r + o.r_h): return True
-    if near(ssd.cdist(rx, cx), o.r_r + o.r_c): return True
-    if near(ssd.cdist(rx, bomb), o.r_r + o.bomb_radius): return True
-    if near(ssd.cdist(rx, key), o.r_r + o.key_radius): return True
-    for objx in (hx, cx, bomb, key):
-        for i in range(o.Nr):
-            rel = objx - rx[i][None, :]
-            sv = o.S.dot(rel.T)
-            q = (rel ** 2).sum(axis=1)[None, :] - sv ** 2
-            lo = (sv < -eps) | (sv > o.sensor_range + eps) | (q > o.r_r ** 2 + eps)
-            hi = (sv < eps) | (sv > o.sensor_range - eps) | (q > o.r_r ** 2 - eps)
-            if np.any(lo != hi):
-                return True
-            svm = np.where(hi, np.inf, sv)
-            if svm.shape[1] >= 2:
-                part = np.sort(svm, axis=1)
-                two = np.isfinite(part[:, 1])
-                if np.any(part[two, 1] - part[two, 0] < eps):
-                    return True
-    cx2 = cx + cv
-    if near(cx2, 0.0) or near(cx2, 1.0):
-        return True
-    return False

@@ -26,10 +26,43 @@ WW_CASES = {
     "ww_c2": (dict(n_pursuers=5, n_evaders=5), 11, 3, 120, 0.5),
     "ww_dense": (dict(n_pursuers=5, n_evaders=5, n_coop=1, radius=0.04, sensor_range=0.3), 12, 0, 120, 1.0),
     "ww_c4": (dict(n_pursuers=20, n_evaders=50, n_poison=50), 13, 40000, 16, 0.5),
+    "ww_c4_long": (dict(n_pursuers=20, n_evaders=50, n_poison=50), 15, 123456, 64, 0.7),
     "ww_global_nospeed": (dict(n_pursuers=3, n_evaders=4, n_poison=2, n_sensors=7, n_coop=1, radius=0.05,
                                reward_mech='global', speed_features=False, addid=False,
                                obstacle_loc=None), 14, 9, 150, 1.0),
 }
+
+
+class _StateLog(object):
+    """Per-step snapshots of the REFERENCE env's internal state (entry t = state before step t,
+    entry T = final state): the fp32 kernels are teacher-forced from these in the GPU tests."""
+
+    def __init__(self, fn):
+        self.fn, self.rows = fn, []
+
+    def snap(self):
+        self.rows.append(self.fn())
+
+    def arrays(self):
+        return {"st_" + k: np.array([r[k] for r in self.rows]) for k in self.rows[0]}
+
+
+def _ww_state(env):
+    objs = list(env._pursuers) + list(env._evaders) + list(env._poisons)
+    return dict(pos=np.array([a.position for a in objs]), vel=np.array([a.velocity for a in objs]),
+                obst=np.array(env.obstaclesx_No_2).reshape(2), t=env._timesteps,
+                counter=env.np_random.counter)
+
+
+def _hw_state(env):
+    return dict(rx=np.array([a.position for a in env._rescuers]),
+                rv=np.array([a.velocity for a in env._rescuers]),
+                hx=np.array([a.position for a in env._hostages]),
+                cx=np.array([a.position for a in env._criminals]),
+                cv=np.array([a.velocity for a in env._criminals]),
+                bomb=np.array(env.bomb_loc).reshape(2), key=np.array(env.key_loc).reshape(2),
+                saved=np.array(env.curr_host_saved_mask, dtype=bool), gate=bool(env._gate_open),
+                bombed=bool(env._bombed), t=env._timesteps, counter=env.np_random.counter)
 
 
 def gen_waterworld(MAWaterWorld):
@@ -41,10 +74,13 @@ def gen_waterworld(MAWaterWorld):
         arng = np.random.RandomState(seed)
         actions = (arng.randn(T, Np, 2) * std).astype(np.float32).astype(np.float64)
         obs, rew, done, info = [], [], [], []
+        st = _StateLog(lambda: _ww_state(env))
         for t in range(T):
+            st.snap()
             o, r, d, i = env.step(actions[t])
             obs.append(np.array(o)); rew.append(np.array(r)); done.append(d)
             info.append([i['evcatches'], i['pocatches']])
+        st.snap()
         cfg = {k: (None if v is None else v) for k, v in kw.items()}
         np.savez_compressed(
             os.path.join(GOLDEN, name + ".npz"), config=json.dumps(cfg), seed=seed, env_id=env_id,
@@ -53,7 +89,7 @@ def gen_waterworld(MAWaterWorld):
             final_px=np.array([p.position for p in env._pursuers]),
             final_ex=np.array([p.position for p in env._evaders]),
             final_ov=np.array([p.velocity for p in env._poisons]),
-            counter=env.np_random.counter)
+            counter=env.np_random.counter, **st.arrays())
         print(name, "catches", np.array(info).sum(0), "draws", env.np_random.counter)
 
 
@@ -138,20 +174,23 @@ def gen_hostage(ContinuousHostageWorld):
         arng = np.random.RandomState(seed)
         actions = (arng.randn(T, Nr, 2) * std).astype(np.float32).astype(np.float64)
         obs, rew, done, info, reset_at, reset_obs = [], [], [], [], [], []
+        st = _StateLog(lambda: _hw_state(env))
         for t in range(T):
+            st.snap()
             o, r, d, i = env.step(actions[t])
             obs.append(np.array(o)); rew.append(np.array(r)); done.append(d)
             info.append([i['ho_saved'], i['cr_encs']])
             if d:
                 reset_at.append(t)
                 reset_obs.append(np.array(env.reset()))
+        st.snap()
         np.savez_compressed(
             os.path.join(GOLDEN, name + ".npz"), args=np.array(args), config=json.dumps(kw), seed=seed,
             env_id=env_id, actions=actions, obs0=obs0, obs=np.array(obs), rew=np.array(rew),
             done=np.array(done), info=np.array(info, dtype=np.int32),
             reset_at=np.array(reset_at, dtype=np.int32),
             reset_obs=np.array(reset_obs) if reset_obs else np.zeros((0,) + obs0.shape),
-            counter=env.np_random.counter)
+            counter=env.np_random.counter, **st.arrays())
         print(name, "saved/encs", np.array(info).sum(0), "dones", int(np.sum(done)), "draws", env.np_random.counter)
 
 

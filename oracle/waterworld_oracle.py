@@ -3,7 +3,7 @@
 This is a restatement -- not a copy -- of the algorithm in the reference file
 ``madrl_environments/pursuit/waterworld.py`` (cited per function below, ``ww:LINE``).  State is
 held as plain arrays instead of ``Archea`` objects.  It is pinned against the real reference
-classes (imported through ``oracle/refshim.py``) by ``tests/test_oracle_vs_reference.py`` and by
+classes (imported through ``oracle/refshim.py``) by ``tests/test_waterworld_oracle.py`` (marker ``reference``) and by
 the golden vectors in ``tests/golden`` produced by ``oracle/make_golden.py``; on identical
 injected random streams the two agree bit for bit in float64.
 
@@ -202,55 +202,3 @@ class WaterworldOracle(object):
         self.t += 1                                                            # ww:433
         done = self.t >= self.timestep_limit
         return obs, rewards, done, dict(evcatches=len(ev_caught), pocatches=len(po_caught))
-
-
-# ---------------------------------------------------------------------------------------------
-# Fragility analysis (test helper, not part of the restatement): would any branch decision of a
-# step started from `state` flip if every compared quantity moved by up to `eps`?  The fp32
-# engine is compared with this float64 oracle only on transitions that are not fragile.
-# ---------------------------------------------------------------------------------------------
-def fragile_step(o, state, action, eps):
-    """True if the step from `state` with `action` contains a comparison within `eps` of its
-    threshold (exact ties between exactly-representable values are not counted)."""
-    def near(a, b):
-        d = np.abs(np.asarray(a, dtype=np.float64) - b)
-        return bool(np.any((d < eps) & (d > 0)))
-
-    px = np.asarray(state['px'], float); pv = np.asarray(state['pv'], float)
-    ex = np.asarray(state['ex'], float); ev = np.asarray(state['ev'], float)
-    ox = np.asarray(state['ox'], float); ov = np.asarray(state['ov'], float)
-    obst = np.asarray(state['obst'], float)
-    act = np.asarray(action, float).reshape(o.Np, 2) * o.action_scale
-    pv = pv + act
-    px = px + pv
-    if near(px, 0.0) or near(px, 1.0):
-        return True
-    px = np.clip(px, 0, 1)
-    if near(ssd.cdist(px, obst), o.r_p + o.obstacle_radius): return True
-    if near(ssd.cdist(ex, obst), o.r_e + o.obstacle_radius): return True
-    if near(ssd.cdist(ox, obst), o.r_po + o.obstacle_radius): return True
-    if near(ssd.cdist(px, ex), o.r_p + o.r_e): return True
-    if near(ssd.cdist(px, ox), o.r_p + o.r_po): return True
-    # sensors: interval evaluation of the three-clause predicate + argmin ties
-    for objx, same in ((obst, False), (ex, False), (ox, False), (px, True)):
-        for i in range(o.Np):
-            rel = objx - px[i][None, :]
-            sv = o.S.dot(rel.T)
-            q = (rel ** 2).sum(axis=1)[None, :] - sv ** 2
-            lo = (sv < -eps) | (sv > o.sensor_range + eps) | (q > o.r_p ** 2 + eps)
-            hi = (sv < eps) | (sv > o.sensor_range - eps) | (q > o.r_p ** 2 - eps)
-            if same:
-                lo[:, i] = hi[:, i] = True
-            if np.any(lo != hi):
-                return True
-            svm = np.where(hi, np.inf, sv)
-            if svm.shape[1] >= 2:
-                part = np.sort(svm, axis=1)
-                two = np.isfinite(part[:, 1])
-                if np.any(part[two, 1] - part[two, 0] < eps):
-                    return True
-    ex2 = ex + ev
-    ox2 = ox + ov
-    if near(ex2, 0.0) or near(ex2, 1.0) or near(ox2, 0.0) or near(ox2, 1.0):
-        return True
-    return False

@@ -150,39 +150,46 @@ def test_waterworld_fp32_build_tracks_fp64_build():
 
 
 @pytest.mark.parametrize("variant", sorted(VARIANTS))
-@pytest.mark.parametrize("name,E,T,min_frac", [("c2", 12, 12, 0.85), ("dense", 10, 12, 0.85), ("c4", 2, 4, 0.3)])
+@pytest.mark.parametrize("name,E,T,min_frac", [("c2", 12, 12, 0.95), ("dense", 10, 12, 0.95), ("c4", 2, 4, 0.85)])
 def test_waterworld_fp32_single_step_teacher_forced(variant, name, E, T, min_frac):
     """The fp32 instantiation, one step at a time from its own fp32 states, against the float64 oracle
-    (tolerance 1e-5, transitions with a comparison within 3e-7 of its threshold skipped) -- the
-    GPU test's methodology at small size."""
+    (tolerance 1e-5, per-predicate exclusion of comparisons within 3e-7 of their threshold) -- the
+    GPU test's methodology (tests/teacher_forced.py) at small size."""
+    import teacher_forced as TF
     from emu.driver import EmuWaterworld
-    from oracle.waterworld_oracle import fragile_step
-    cfg, seed = WW[name], 99
-    eng = EmuWaterworld(E, seed=seed, fp64=False, defines=VARIANTS[variant], **cfg)
+    cfg = WW[name]
+    eng = EmuWaterworld(E, seed=99, fp64=False, defines=VARIANTS[variant], **cfg)
     eng.reset()
-    Np = cfg['n_pursuers']
-    rs = np.random.RandomState(3)
-    orc = WaterworldOracle(rng=Stream(seed, 0), **cfg)
-    checked = 0
-    for t in range(T):
-        act = (rs.randn(1, E, Np, 2) * 0.7).astype(np.float32)
-        pre = [eng.state(e) for e in range(E)]
-        obs, rew, done, info = eng.rollout(act, auto_reset=False)
-        for e in range(E):
-            if fragile_step(orc, pre[e], act[0, e], 3e-7):
-                continue
-            orc.np_random = Stream(seed, e, counter=pre[e]['counter'])
-            orc.set_state(pre[e])
-            oo, rr, dd, ii = orc.step(act[0, e].astype(np.float64))
-            assert [ii['evcatches'], ii['pocatches']] == list(info[0, e]), (t, e)
-            assert np.abs(np.array(oo) - obs[0, e]).max() <= 1e-5, (t, e)
-            assert np.abs(rr - rew[0, e]).max() <= 1e-5, (t, e)
-            post = eng.state(e)
-            assert post['counter'] == orc.np_random.counter
-            for k in ('px', 'pv', 'ex', 'ev', 'ox', 'ov'):
-                assert np.abs(post[k] - getattr(orc, k)).max() <= 1e-5, (t, e, k)
-            checked += 1
-    assert checked > min_frac * E * T, checked
+    log = TF.ww_self_teacher_forced(TF.EmuAdapter(eng, "ww"), cfg, 99, T, 0.7, "emu_ww_" + name)
+    assert log.checked_frac >= min_frac and log.obs_frac >= 0.999, log.d
+
+
+@pytest.mark.parametrize("name", ["ww_c2", "ww_dense", "ww_c4", "ww_global_nospeed"])
+def test_waterworld_fp32_teacher_forced_from_reference_states(name):
+    """fp32 instantiation replayed from the REAL reference's recorded float64 states (tests/golden)."""
+    import teacher_forced as TF
+    from emu.driver import EmuWaterworld
+    g, cfg = _golden(name)
+    if cfg.get("obstacle_loc", 0) is not None and "obstacle_loc" in cfg:
+        cfg["obstacle_loc"] = np.array(cfg["obstacle_loc"])
+    eng = EmuWaterworld(1, seed=int(g["seed"]), env_id_base=int(g["env_id"]), fp64=False, **cfg)
+    eng.reset()
+    log = TF.ww_golden_teacher_forced(TF.EmuAdapter(eng, "ww"), g, cfg, "emu_golden_" + name)
+    assert log.checked_frac >= 0.95 and log.obs_frac >= 0.999, log.d
+
+
+@pytest.mark.parametrize("name", ["hw_c5", "hw_c5_local", "hw_dense", "hw_k12"])
+def test_hostage_fp32_teacher_forced_from_reference_states(name):
+    import teacher_forced as TF
+    from emu.driver import EmuHostage
+    g, kw = _golden(name)
+    if 'key_loc' in kw:
+        kw['key_loc'] = np.array(kw['key_loc'])
+    args = tuple(int(a) for a in g["args"])
+    eng = EmuHostage(1, *args, seed=int(g["seed"]), env_id_base=int(g["env_id"]), fp64=False, **kw)
+    eng.reset()
+    log = TF.hw_golden_teacher_forced(TF.EmuAdapter(eng, "hw"), g, args, kw, "emu_golden_" + name)
+    assert log.checked_frac >= 0.95 and log.obs_frac >= 0.999, log.d
 
 
 # ------------------------------------------------------------------------------------ Pursuit
