@@ -99,7 +99,8 @@ int madrl_ww_destroy(madrl_ww* h);
 void* madrl_ww_state_ptr(madrl_ww* h);
 /* seed(): new key, draw counters reset to 0 (waterworld.py:135-137 creates a fresh generator). */
 int madrl_ww_seed(madrl_ww* h, uint64_t seed, void* stream);
-/* Launch geometry override (0 = library default): warps (= envs) per block <= 4, blocks per SM. */
+/* Launch geometry override (0 = library default): resident blocks per SM.  Blocks are one warp (= one
+ * env) since round 2; `warps_per_block` is accepted for ABI stability and ignored. */
 int madrl_ww_set_launch(madrl_ww* h, int warps_per_block, int blocks_per_sm);
 /* Fused per-rollout exchange for env-sharded multi-GPU runs: after this call every rollout also
  * stores its reward / done / info rows into slot `slot` of each of the `n_dest` listed gather

@@ -45,25 +45,15 @@ __device__ __forceinline__ double real_inf<double>() {
 }
 
 // Streaming (evict-first) store for write-once trajectory tensors.
-#ifndef MADRL_PLAIN_STORES
-#define MADRL_PLAIN_STORES 0   // 1: ordinary write-back stores instead (experiment)
-#endif
 template <typename T>
 __device__ __forceinline__ void store_stream(T* p, T v) {
-#if MADRL_PLAIN_STORES
-  *p = v;
-#else
   __stcs(p, v);
-#endif
 }
 
 // Experiment: launch the warp-per-env kernels as 32-thread blocks.  The env index then derives from
 // blockIdx alone, so ptxas can prove the persistent loop and every branch on warp-uniform values
 // uniform: the BRA.DIV guards in front of the warp collectives disappear, loop bookkeeping moves to
 // the uniform datapath and the register count drops (Waterworld C2: 72 regs + spills -> 56, none).
-#ifndef MADRL_ONE_WARP_BLOCKS
-#define MADRL_ONE_WARP_BLOCKS 0
-#endif
 
 // Kernels are launched through one macro and the PTX-level helpers below sit behind one guard so
 // that the test-only warp emulator (tests/emu: the kernels compiled by g++ against a fake

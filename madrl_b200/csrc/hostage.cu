@@ -61,50 +61,17 @@ __device__ __forceinline__ real unit_at(uint64_t seed, uint32_t env_id, uint64_t
   return (real)(stream_word(seed, env_id, 0u, n) >> 8) * (real)(1.0 / 16777216.0);
 }
 
-#ifndef MADRL_HW_DEFERRED_TAIL
-// 1: the observation tail of every rescuer is written once per step from the any-collision masks
-// the reward logic computes anyway, instead of a ballot + a 6-lane store per rescuer.
-#define MADRL_HW_DEFERRED_TAIL 1
-#endif
-#ifndef MADRL_HW_LEAN_SENSE
-// 1 (experiment): which rescuers have the key / the bomb within sensing range is two ballots per
-// step (from the distances the collision test computes anyway) instead of per-rescuer arithmetic; a
-// rescuer with no criminal in range skips the velocity shuffles and the feature arithmetic.
-#define MADRL_HW_LEAN_SENSE 0
-#endif
-#ifndef MADRL_HW_SPLIT
-// 1 (experiment): the rescuers live in their own four registers (lane i = rescuer i) and the
-// per-lane object registers hold only what is sensed and collided with -- criminals, then hostages.
-// Allies are never emitted (hw:395-397), so nothing is lost, and C5's 16 + 16 objects fit ONE chunk
-// of 32 lanes instead of two (10 rescuers + 32 objects = 42): one geometry / ballot / scan pass per
-// rescuer instead of two.  OPL then counts chunks of n_bad + n_hostages.
-#define MADRL_HW_SPLIT 0
-#endif
-#ifndef MADRL_HW_ONE_WARP_BLOCKS
-#define MADRL_HW_ONE_WARP_BLOCKS MADRL_ONE_WARP_BLOCKS   // see common.cuh
-#endif
 template <typename real, int OPL, int KCH, int KC>
-#if MADRL_HW_ONE_WARP_BLOCKS
 __global__ void __launch_bounds__(32, (OPL <= 2 ? 28 : 16))
-#else
-__global__ void __launch_bounds__(128, (OPL <= 2 ? 7 : 4))
-#endif
 hw_kernel(const __grid_constant__ HWParams<real> p) {
   const real INF = real_inf<real>();
   const int K = KC > 0 ? KC : p.K;
-#if MADRL_HW_ONE_WARP_BLOCKS
   const int lane = threadIdx.x;
   const int warp_global = blockIdx.x;
   const int warp_stride = gridDim.x;
-#else
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  const int warp_stride = gridDim.x * warps_per_block;
-#endif
   const int cLo = p.Nr, hLo = p.Nr + p.Nc, Nall = p.Nall;
-  // first object index held in the per-lane object registers (see MADRL_HW_SPLIT)
-  const int obase = MADRL_HW_SPLIT ? p.Nr : 0;
+  // first object index held in the per-lane object registers (see 1)
+  const int obase = p.Nr;
 
   real cull2_l[OPL], coll2_l[OPL];
   unsigned mC[OPL], mH[OPL];   // warp-uniform class masks (criminals, hostages) per object chunk
@@ -124,9 +91,6 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
     sx_l[kc] = (k < K) ? p.sensors[k] : (real)0;
     sy_l[kc] = (k < K) ? p.sensors[K + k] : (real)0;
   }
-#if !MADRL_HW_DEFERRED_TAIL
-  const int n_tail = 5 + (p.addid ? 1 : 0);
-#endif
   typedef typename HVec2<real>::type V2;
 
   for (int e = warp_global; e < p.E; e += warp_stride) {
@@ -147,12 +111,8 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
       col[c] = 0u;
       sav[c] = (o >= hLo && o < Nall) ? (p.saved[(size_t)e * p.Nh + (o - hLo)] != 0) : false;
     }
-#if MADRL_HW_SPLIT
     real rpx = 0, rpy = 0, rpvx = 0, rpvy = 0;   // rescuer `lane`
     if (lane < p.Nr) { rpx = rec[lane]; rpy = rec[Nall + lane]; rpvx = rec[2 * Nall + lane]; rpvy = rec[3 * Nall + lane]; }
-#else
-    real &rpx = x[0], &rpy = y[0], &rpvx = vx[0], &rpvy = vy[0];   // rescuers are objects 0..Nr-1 of chunk 0
-#endif
     real kx = p.fixed[4 * (size_t)e], ky = p.fixed[4 * (size_t)e + 1];
     real bx = p.fixed[4 * (size_t)e + 2], by = p.fixed[4 * (size_t)e + 3];
     int flags = p.flags[e];
@@ -187,7 +147,6 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
             }
           } else { kx = p.key_x; ky = p.key_y; }
           flags = 4;   // gate closed, not bombed, key known
-#if MADRL_HW_SPLIT
           if (lane < p.Nr) {                                                 // hw:155-159
             const uint64_t b = n + 2 * (uint64_t)lane;
             rpx = unit_at<real>(p.seed, env_id, b);
@@ -195,12 +154,11 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
             rpy = yy < (real)0.55 ? (real)0.55 : (yy > (real)0.95 ? (real)0.95 : yy);
             rpvx = 0; rpvy = 0;
           }
-#endif
 #pragma unroll
           for (int c = 0; c < OPL; ++c) {
             const int o = obase + lane + 32 * c;
             sav[c] = false;
-            if (!MADRL_HW_SPLIT && o < cLo) {                                // hw:155-159
+            if (!1 && o < cLo) {                                // hw:155-159
               const uint64_t b = n + 2 * (uint64_t)o;
               x[c] = unit_at<real>(p.seed, env_id, b);
               const real yy = unit_at<real>(p.seed, env_id, b + 1);
@@ -258,21 +216,14 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
         // ---- key / bomb collisions of every rescuer up front (the obs tail needs the post-step
         //      gate flag): hw:286-296 ----------------------------------------------------------------
         unsigned coll_ke, coll_bo;
-#if MADRL_HW_LEAN_SENSE
         unsigned key_near, bomb_near;
-#endif
         {
           const real dkx = rpx - kx, dky = rpy - ky, dbx = rpx - bx, dby = rpy - by;
-#if MADRL_HW_LEAN_SENSE
           const real dk2 = dkx * dkx + dky * dky, db2 = dbx * dbx + dby * dby;
           coll_ke = __ballot_sync(FULL_MASK, lane < p.Nr && dk2 <= p.coll2_key);
           coll_bo = __ballot_sync(FULL_MASK, lane < p.Nr && db2 <= p.coll2_bomb);
           key_near = __ballot_sync(FULL_MASK, lane < p.Nr && dk2 <= p.cull2);    // conservative range cull;
           bomb_near = __ballot_sync(FULL_MASK, lane < p.Nr && db2 <= p.cull2);   // the exact tests decide
-#else
-          coll_ke = __ballot_sync(FULL_MASK, lane < p.Nr && dkx * dkx + dky * dky <= p.coll2_key);
-          coll_bo = __ballot_sync(FULL_MASK, lane < p.Nr && dbx * dbx + dby * dby <= p.coll2_bomb);
-#endif
         }
         const bool gate_post = gate_pre || (coll_ke != 0u);
         // ---- sense: one rescuer at a time -----------------------------------------------------------
@@ -289,47 +240,27 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
             bK[kc] = bB[kc] = bC[kc] = bH[kc] = INF;
             iC[kc] = 0;
             const real sx = sx_l[kc], sy = sy_l[kc];
-#if MADRL_HW_LEAN_SENSE
             if (!gate_pre && ((key_near >> pi) & 1u)) {                           // hw:343-345
-#else
-            if (!gate_pre && kd2 <= p.cull2) {                                    // hw:343-345
-#endif
               const real sv = sx * krx + sy * kry;
               const bool ok = !((sv < (real)0) | (sv > p.range) | (kd2 - sv * sv > p.r_r2));
               bK[kc] = ok ? sv : INF;
             }
-#if MADRL_HW_LEAN_SENSE
             if ((bomb_near >> pi) & 1u) {
-#else
-            if (bd2 <= p.cull2) {
-#endif
               const real sv = sx * brx + sy * bry;
               const bool ok = !((sv < (real)0) | (sv > p.range) | (bd2 - sv * sv > p.r_r2));
               bB[kc] = ok ? sv : INF;
             }
           }
-#if !MADRL_HW_DEFERRED_TAIL
-          unsigned hitC = 0u, hitH = 0u;
-#endif
-#if MADRL_HW_LEAN_SENSE
           unsigned candC = 0u;   // warp-uniform: criminals within range of this rescuer
-#endif
 #pragma unroll
           for (int c = 0; c < OPL; ++c) {
             const real rx = x[c] - mx, ry = y[c] - my;
             const real d2 = rx * rx + ry * ry;
             // saved hostages are invisible (pre-step mask, hw:301) but still collide (hw:269-275)
             const unsigned cm = __ballot_sync(FULL_MASK, d2 <= cull2_l[c] && !sav[c]);
-#if MADRL_HW_LEAN_SENSE
             candC |= cm & mC[c];
-#endif
             const bool hit = d2 <= coll2_l[c];
             if (hit) col[c] |= 1u << pi;
-#if !MADRL_HW_DEFERRED_TAIL
-            const unsigned hb = __ballot_sync(FULL_MASK, hit);
-            hitC |= hb & mC[c];
-            hitH |= hb & mH[c];
-#endif
 #pragma unroll
             for (int kc = 0; kc < KCH; ++kc) {
               const real sx = sx_l[kc], sy = sy_l[kc];
@@ -359,7 +290,6 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
             // features hw:395-397: [criminal dist, criminal speed, hostage dist, key dist, bomb dist]
             const int k = lane + 32 * kc;
             const real z = (real)0;
-#if MADRL_HW_LEAN_SENSE
             real fC = z, sC = z;
             if (candC != 0u) {
               real oCx = z, oCy = z;
@@ -376,39 +306,11 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
               real* o = obs_row + 32 * kc;
               store_stream(o + 0 * K, fC);
               store_stream(o + 1 * K, sC);
-#else
-            real oCx, oCy;
-            if (OPL == 1) {
-              oCx = __shfl_sync(FULL_MASK, vx[0], iC[kc]); oCy = __shfl_sync(FULL_MASK, vy[0], iC[kc]);
-            } else {
-              oCx = oCy = z;
-#pragma unroll
-              for (int c = 0; c < OPL; ++c) {
-                const real cx_ = __shfl_sync(FULL_MASK, vx[c], iC[kc] & 31), cy_ = __shfl_sync(FULL_MASK, vy[c], iC[kc] & 31);
-                if ((iC[kc] >> 5) == c) { oCx = cx_; oCy = cy_; }
-              }
-            }
-            if (k < K) {
-              real* o = obs_row + 32 * kc;
-              const bool hC = bC[kc] < INF;
-              store_stream(o + 0 * K, hC ? bC[kc] : z);
-              store_stream(o + 1 * K, hC ? sx * (oCx - mvx) + sy * (oCy - mvy) : z);
-#endif
               store_stream(o + 2 * K, bH[kc] < INF ? bH[kc] : z);
               store_stream(o + 3 * K, bK[kc] < INF ? bK[kc] : z);
               store_stream(o + 4 * K, bB[kc] < INF ? bB[kc] : z);
             }
           }
-#if !MADRL_HW_DEFERRED_TAIL
-          // tail hw:406-421: coll_ho, coll_cr, coll_key, coll_bomb, gate_open (post), id -- one
-          // branch-free store
-          if (lane < n_tail) {
-            const unsigned bits = (hitH ? 1u : 0u) | (hitC ? 2u : 0u) | (((coll_ke >> pi) & 1u) << 2) |
-                                  (((coll_bo >> pi) & 1u) << 3) | (gate_post ? 16u : 0u);
-            const real tv = lane < 5 ? (real)((bits >> lane) & 1u) : (real)(pi + 1);
-            store_stream(obs_row + 5 * K, tv);
-          }
-#endif
         }
         // ---- process collisions + rewards: hw:274-284, 368-392 ---------------------------------------
         unsigned whoH = 0u, whoEnc = 0u, whoC = 0u;
@@ -442,7 +344,6 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
         whoH = __reduce_or_sync(FULL_MASK, whoH);
         whoEnc = __reduce_or_sync(FULL_MASK, whoEnc);
         whoC = __reduce_or_sync(FULL_MASK, whoC);
-#if MADRL_HW_DEFERRED_TAIL
         // tail hw:406-421 of every rescuer's row: coll_ho, coll_cr, coll_key, coll_bomb, gate_open
         // (post), id; lane i writes rescuer i's.  whoEnc / whoC are exactly the any-collision masks.
         if (lane < p.Nr) {
@@ -454,7 +355,6 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
           store_stream(tp + 4, gate_post ? (real)1 : (real)0);
           if (p.addid) store_stream(tp + 5, (real)(lane + 1));
         }
-#endif
         if (coll_bo) flags |= 2;
         if (coll_ke) flags |= 1;
         const bool bombed = flags & 2;
@@ -507,9 +407,7 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
       if (o < Nall) { rec[o] = x[c]; rec[Nall + o] = y[c]; rec[2 * Nall + o] = vx[c]; rec[3 * Nall + o] = vy[c]; }
       if (o >= hLo && o < Nall) p.saved[(size_t)e * p.Nh + (o - hLo)] = sav[c] ? 1 : 0;
     }
-#if MADRL_HW_SPLIT
     if (lane < p.Nr) { rec[lane] = rpx; rec[Nall + lane] = rpy; rec[2 * Nall + lane] = rpvx; rec[3 * Nall + lane] = rpvy; }
-#endif
     if (lane == 0) {
       p.fixed[4 * (size_t)e] = kx; p.fixed[4 * (size_t)e + 1] = ky;
       p.fixed[4 * (size_t)e + 2] = bx; p.fixed[4 * (size_t)e + 3] = by;
@@ -653,19 +551,14 @@ static real hw_exact_sq_threshold(double thr_d) {
 
 template <typename real, int OPL, int KCH, int KC>
 static int hw_launch_inst(madrl_hostage* h, const HWParams<real>& p, cudaStream_t stream) {
-#if MADRL_HW_ONE_WARP_BLOCKS
-  const int wpb = 1;
-#else
-  const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 4;
-#endif
   const auto kfn = hw_kernel<real, OPL, KCH, KC>;
   int resident = 0;
-  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, wpb * 32, 0));
+  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, 32, 0));
   if (resident < 1) resident = 1;
   if (h->blocks_per_sm > 0 && h->blocks_per_sm < resident) resident = h->blocks_per_sm;
-  int grid = (p.E + wpb - 1) / wpb;
+  int grid = p.E;
   if (grid > h->sms * resident) grid = h->sms * resident;
-  MADRL_LAUNCH(kfn, grid, wpb * 32, 0, stream, p);
+  MADRL_LAUNCH(kfn, grid, 32, 0, stream, p);
   g_launches.fetch_add(1);
   MADRL_CUDA_CHECK(cudaGetLastError());
   return MADRL_OK;
@@ -704,7 +597,7 @@ static int hw_launch(madrl_hostage* h, int mode, int T, const void* actions, voi
   p.ctr = (uint64_t*)(st + h->lay.rng_counter); p.sensors = (const real*)(st + h->lay.sensors);
   p.actions = (const real*)actions; p.obs = (real*)obs; p.rew = (real*)rew;
   p.done = done; p.info = info; p.mask = mask;
-  const int opl = ((MADRL_HW_SPLIT ? p.Nall - p.Nr : p.Nall) + 31) / 32, kch = (p.K + 31) / 32;
+  const int opl = (p.Nall - p.Nr + 31) / 32, kch = (p.K + 31) / 32;
 #define MADRL_HW_CASE(O, KH, KC_) return hw_launch_inst<real, O, KH, KC_>(h, p, stream)
   if (p.K == 30) {
     if (opl == 1) MADRL_HW_CASE(1, 1, 30);

@@ -79,34 +79,12 @@ __device__ __forceinline__ double numpy_mean(const double* a, int n) {
 
 // EPL = evaders per lane (ceil(Ne/32)); CPL = window cells per lane (ceil(R*R/32));
 // RC = compile-time obs_range (0 = runtime p.R).
-#ifndef MADRL_PE_MINBLOCKS
-#define MADRL_PE_MINBLOCKS 7   // resident 128-thread blocks per SM requested (7 -> 72 registers)
-#endif
-#ifndef MADRL_PE_PHILOX_CACHE
-// 1 (experiment): the evader-action draws (one stream word per live evader per step, pe:238-241) come
-// from a per-warp cache of 32 Philox blocks = 128 consecutive words in shared memory, refilled (all
-// lanes compute one block each) when the words of the coming step fall outside it -- every ~4 steps
-// at 30 evaders -- instead of every lane running the 10 Philox rounds for a single word every step.
-#define MADRL_PE_PHILOX_CACHE 0
-#endif
-#ifndef MADRL_PE_ONE_WARP_BLOCKS
-#define MADRL_PE_ONE_WARP_BLOCKS MADRL_ONE_WARP_BLOCKS   // see common.cuh
-#endif
 template <int EPL, int CPL, int RC>
-#if MADRL_PE_ONE_WARP_BLOCKS
-__global__ void __launch_bounds__(32, 4 * MADRL_PE_MINBLOCKS) pe_kernel(const __grid_constant__ PEParams p) {
+__global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEParams p) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   const int lane = threadIdx.x, wib = 0;
   const int warp_global = blockIdx.x;
   const int warp_stride = gridDim.x;
-#else
-__global__ void __launch_bounds__(128, MADRL_PE_MINBLOCKS) pe_kernel(const __grid_constant__ PEParams p) {
-  extern __shared__ __align__(16) uint32_t smem_u32[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int warps_per_block = blockDim.x >> 5;
-  const int warp_global = blockIdx.x * warps_per_block + wib;
-  const int warp_stride = gridDim.x * warps_per_block;
-#endif
   const int R = RC > 0 ? RC : p.R, RR = R * R, xs = p.xs, ys = p.ys, ncell = xs * ys;
   const int Np = p.Np, Ne = p.Ne, Nag = Np + Ne;
 
@@ -116,9 +94,7 @@ __global__ void __launch_bounds__(128, MADRL_PE_MINBLOCKS) pe_kernel(const __gri
   const uint32_t lut_a = smem_addr(smem_u32);
   const uint32_t cell_a = lut_a + 1024u + (uint32_t)wib * (uint32_t)p.smem_per_warp;
   const uint32_t stale_a = cell_a + 4u * (uint32_t)p.cells_pad;
-#if MADRL_PE_PHILOX_CACHE
   const uint32_t wcache_a = cell_a + (uint32_t)p.smem_per_warp - 512u;   // last 512 bytes of the warp's region
-#endif
   const float my_idv = (lane < p.Np) ? p.idv[lane] : 0.0f;   // lane i keeps float32(i / Np)
 
   // per-lane window cell offsets
@@ -153,9 +129,7 @@ __global__ void __launch_bounds__(128, MADRL_PE_MINBLOCKS) pe_kernel(const __gri
     const uint8_t* map = p.maps + (size_t)map_id * ncell;
     for (int i = lane; i < Np * RR; i += 32) sts_u16(stale_a + 2u * i, p.stale[(size_t)e * Np * RR + i]);
     bool rebuild = true;   // cell words must be (re)built from map + positions
-#if MADRL_PE_PHILOX_CACHE
     uint64_t cblk = ~0ull;   // first cached Philox block (warp-uniform); ~0 = cache empty
-#endif
 
     float* obs_t = p.obs + (size_t)e * Np * p.D;
     float* rew_t = p.rew + (size_t)e * Np + lane;
@@ -243,7 +217,6 @@ __global__ void __launch_bounds__(128, MADRL_PE_MINBLOCKS) pe_kernel(const __gri
           }
           // ---- move live evaders, one stream draw each in index order: pe:238-241, ct:16 -------
           int base_rank = 0;
-#if MADRL_PE_PHILOX_CACHE
           {
             int n_draws = 0;
 #pragma unroll
@@ -260,18 +233,13 @@ __global__ void __launch_bounds__(128, MADRL_PE_MINBLOCKS) pe_kernel(const __gri
               __syncwarp();
             }
           }
-#endif
 #pragma unroll
           for (int c = 0; c < EPL; ++c) {
             const bool alive = (live[c] >> lane) & 1u;
             const int rank = base_rank + __popc(live[c] & lanemask_lt());
             if (alive) {
-#if MADRL_PE_PHILOX_CACHE
               const uint32_t word = lds_u32(wcache_a + 4u * (uint32_t)(ctr + (uint64_t)rank - 4u * cblk));
               const int a = u32_to_range(word, 0, 5);
-#else
-              const int a = u32_to_range(stream_word(p.seed, env_id, 0u, ctr + (uint64_t)rank), 0, 5);
-#endif
               const int dx = (a == 0) ? -1 : (a == 1 ? 1 : 0), dy = (a == 2) ? 1 : (a == 3 ? -1 : 0);
               const int nx = ex[c] + dx, ny = ey[c] + dy;
               const uint32_t cur = cell_a + 4u * (ex[c] * ys + ey[c]), nxt = cell_a + 4u * (nx * ys + ny);
@@ -571,23 +539,18 @@ extern "C" int madrl_pursuit_set_params(madrl_pursuit* h, double catchr, double 
 
 template <int EPL, int CPL, int RC>
 static int pe_launch_inst(madrl_pursuit* h, PEParams& p, cudaStream_t stream) {
-#if MADRL_PE_ONE_WARP_BLOCKS
-  const int wpb = 1;
-#else
-  const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 4;
-#endif
-  const size_t smem = 1024 + (size_t)wpb * p.smem_per_warp;   // block LUT + per-warp regions
+  const size_t smem = 1024 + (size_t)p.smem_per_warp;   // block LUT + per-warp regions
   const auto kfn = pe_kernel<EPL, CPL, RC>;
   MADRL_REQUIRE(smem <= 200 * 1024, "map too large for shared memory (%zu B per block)", smem);
   if (smem > 48 * 1024)
     MADRL_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int resident = 0;
-  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, wpb * 32, smem));
+  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, 32, smem));
   if (resident < 1) resident = 1;
   if (h->blocks_per_sm > 0 && h->blocks_per_sm < resident) resident = h->blocks_per_sm;
-  int grid = (p.E + wpb - 1) / wpb;
+  int grid = p.E;
   if (grid > h->sms * resident) grid = h->sms * resident;
-  MADRL_LAUNCH(kfn, grid, wpb * 32, smem, stream, p);
+  MADRL_LAUNCH(kfn, grid, 32, smem, stream, p);
   g_launches.fetch_add(1);
   MADRL_CUDA_CHECK(cudaGetLastError());
   return MADRL_OK;
@@ -608,7 +571,7 @@ static int pe_launch(madrl_pursuit* h, int mode, int T, const int32_t* actions, 
   const int ncell = c.xs * c.ys, RR = c.obs_range * c.obs_range;
   p.cells_pad = (ncell + 31) / 32 * 32;
   p.smem_per_warp = (int)align_up((size_t)p.cells_pad * 4 + (size_t)c.n_pursuers * RR * 2, 16) +
-                    (MADRL_PE_PHILOX_CACHE ? 512 : 0);   // + the warp's Philox word cache
+                    512;   // + the warp's Philox word cache
   p.constraint_window = c.constraint_window; p.catchr = c.catchr; p.term_pursuit = c.term_pursuit;
   p.urgency = c.urgency_reward;
   p.wall_val = (float)(1.0 / c.layer_norm);           // local_obs[i][0].fill(1.0 / layer_norm): f64 -> f32

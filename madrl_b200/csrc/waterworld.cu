@@ -112,80 +112,24 @@ __device__ __noinline__ Spawn<real> spawn_object(uint64_t seed, uint32_t env_id,
 // OPL = objects per lane (ceil(n_obj / 32)); KCH = sensors per lane (ceil(K / 32));
 // KC = compile-time sensor count (0 = runtime p.K): with KC known the 7 feature-row stores of a
 // pursuer use immediate offsets from one running pointer instead of 64-bit address arithmetic.
-#ifndef MADRL_WW_NO_JD_SHFL
-#define MADRL_WW_NO_JD_SHFL 0    // 1: recompute the candidate's d2 instead of a third shuffle (experiment)
-#endif
-#ifndef MADRL_WW_MERGED_SCAN
-#define MADRL_WW_MERGED_SCAN 0   // 1: single candidate loop with a uniform class branch (experiment)
-#endif
-#ifndef MADRL_WW_DEFERRED_TAIL
-// 1: the per-pursuer "touched an evader / a poison" observation tail (ww:411-428) is written once
-// per step from the pursuer masks the catch logic computes anyway (a pursuer touched an evader iff
-// it is in the encounter set, ww:376; a poison iff it is in the poison-catch set, ww:293) instead of
-// one extra ballot + a 3-lane store per pursuer inside the sensing loop.
-#define MADRL_WW_DEFERRED_TAIL 1
-#endif
-#ifndef MADRL_WW_ONE_WARP_BLOCKS
-#define MADRL_WW_ONE_WARP_BLOCKS MADRL_ONE_WARP_BLOCKS   // see common.cuh
-#endif
-#ifndef MADRL_WW_LEAN_SENSE
-// 1 (experiment, shuffle-scan path): (a) which pursuers have the obstacle within sensing range is
-// one ballot per step (from the distances the rebound test computes anyway) instead of a per-pursuer
-// distance computation; (b) a class without any in-range candidate for this pursuer -- the common
-// case: ~0.6 evaders, ~1.3 poisons, ~0.5 other pursuers are in range on average in C2 -- skips its
-// velocity shuffles, found-tests and feature arithmetic and stores zeros directly.
-#define MADRL_WW_LEAN_SENSE 0
-#endif
-#ifndef MADRL_WW_SKIP_EMPTY_CATCH
-#define MADRL_WW_SKIP_EMPTY_CATCH 0   // 1 (experiment): skip catches / respawn / mask reductions on steps without any collision
-#endif
-#ifndef MADRL_WW_SMEM_MIN_OPL
-// Kernels with at least this many objects per lane stage the objects that survive the range cull
-// in per-warp shared memory slots (ascending object order): the sensor lanes then walk the slots
-// with one broadcast vector load per candidate instead of three shuffles + find-first-set
-// bookkeeping, and fetch the winner's velocity with one load instead of per-chunk shuffles.  Same
-// arithmetic, same candidate order => bit-identical results.  It costs ~25 instructions per pursuer
-// up front and saves ~9 per candidate, so it only pays when a pursuer sees many objects (C4-like
-// configurations); 99 = never.
-#define MADRL_WW_SMEM_MIN_OPL 99
-#endif
-#ifndef MADRL_WW_SMEM_UNROLL
-#define MADRL_WW_SMEM_UNROLL 2     // candidates per slot-loop iteration
-#endif
-#define MADRL_PRAGMA_(x) _Pragma(#x)
-#define MADRL_PRAGMA(x) MADRL_PRAGMA_(x)
-#ifndef MADRL_WW_MINBLOCKS_OPL4
-#define MADRL_WW_MINBLOCKS_OPL4 7   // resident 128-thread blocks per SM requested for 65..128 objects
-#endif
 // PEER = compile the fused multi-GPU exchange in (a separate instantiation, so the single-GPU kernel
 // carries none of its registers).
 template <typename real, int OPL, int KCH, int KC, bool PEER>
-#if MADRL_WW_ONE_WARP_BLOCKS
-__global__ void __launch_bounds__(32, (OPL <= 2 ? 28 : (OPL <= 4 ? 4 * MADRL_WW_MINBLOCKS_OPL4 : 16)))
-#else
-__global__ void __launch_bounds__(128, (OPL <= 2 ? 7 : (OPL <= 4 ? MADRL_WW_MINBLOCKS_OPL4 : 4)))
-#endif
+__global__ void __launch_bounds__(32, (OPL <= 4 ? 28 : 16))
 ww_kernel(const __grid_constant__ WWParams<real> p) {
   const real INF = real_inf<real>();
   const int K = KC > 0 ? KC : p.K;
-#if MADRL_WW_ONE_WARP_BLOCKS
-  // 32-thread blocks: the env index derives from blockIdx alone, so the compiler can prove every
-  // loop and branch on it warp-uniform (experiment: drops the BRA.DIV guards in front of the warp
-  // collectives and moves loop bookkeeping to the uniform datapath).
+  // 32-thread blocks: the env index derives from blockIdx alone, so ptxas can prove every loop and
+  // branch on it warp-uniform -- no BRA.DIV guards in front of the warp collectives, loop bookkeeping
+  // on the uniform datapath, 72 -> 56 registers (measured +4 % on C2/C4, profiles/r2_ab_variants.log).
   const int lane = threadIdx.x;
   const int warp_global = blockIdx.x;
   const int warp_stride = gridDim.x;
-#else
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  const int warp_stride = gridDim.x * warps_per_block;
-#endif
   const int eLo = p.Np, eHi = p.Np + p.Ne, Nall = p.Nall;
-  constexpr bool SMEM = OPL >= MADRL_WW_SMEM_MIN_OPL;
+  constexpr bool SMEM = OPL >= 2;
   extern __shared__ __align__(16) unsigned char ww_smem[];
   // this warp's candidate slots (32-bit shared address)
-  const uint32_t slots = SMEM ? smem_addr(ww_smem) + (MADRL_WW_ONE_WARP_BLOCKS ? 0u : (threadIdx.x >> 5)) * (uint32_t)Nall * CandSlot<real>::kStride : 0u;
+  const uint32_t slots = SMEM ? smem_addr(ww_smem) : 0u;
 
   // ---- per-lane constants: this lane as OBJECT (classes, thresholds) and as SENSOR -----------
   real cull2_l[OPL], coll2_l[OPL];
@@ -208,9 +152,6 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     sy_l[kc] = (k < K) ? p.sensors[K + k] : (real)0;
   }
   const int n_feat = p.speed_features ? 7 : 4;
-#if !MADRL_WW_DEFERRED_TAIL
-  const int n_tail = 2 + (p.addid ? 1 : 0);
-#endif
   typedef typename Vec2<real>::type V2;
 
   for (int e = warp_global; e < p.E; e += warp_stride) {
@@ -301,22 +242,13 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
           pen = p.control_penalty * (p.reward_global ? warp_sum(sq) : sq);
         }
         // ---- obstacle rebound (velocity only): ww:247-270 ----------------------------------------
-#if MADRL_WW_LEAN_SENSE
-        unsigned obst_mask = 0u;   // pursuers with the obstacle inside the conservative sensing range
-#endif
 #pragma unroll
         for (int c = 0; c < OPL; ++c) {
           const bool oE = (mE[c] >> lane) & 1u, oP = (mP[c] >> lane) & 1u, oU = (mU[c] >> lane) & 1u;
           const real thr = oU ? p.obst2_p : (oE ? p.obst2_e : (oP ? p.obst2_po : (real)-1));
           const real kf = oP ? (real)-1 : (real)-0.5;                  // ww:254,262,270
           const real dx = x[c] - obx, dy = y[c] - oby;
-#if MADRL_WW_LEAN_SENSE
-          const real do2 = dx * dx + dy * dy;
-          if (c == 0) obst_mask = __ballot_sync(FULL_MASK, lane < p.Np && do2 <= p.cull2);
-          if (do2 <= thr) { vx[c] = kf * vx[c]; vy[c] = kf * vy[c]; }
-#else
           if (dx * dx + dy * dy <= thr) { vx[c] = kf * vx[c]; vy[c] = kf * vy[c]; }
-#endif
         }
         // ---- sense: one pursuer at a time -----------------------------------------------------
         real* obs_row = obs_t;
@@ -332,19 +264,12 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
           for (int kc = 0; kc < KCH; ++kc) {
             bO[kc] = bE[kc] = bP[kc] = bU[kc] = INF;
             iE[kc] = iP[kc] = iU[kc] = 0;
-#if MADRL_WW_LEAN_SENSE
-            if ((obst_mask >> pi) & 1u) {   // warp-uniform; the exact tests below decide
-#else
             if (od2 <= p.cull2) {   // the obstacle is sensed like a point object (pursuer radius only)
-#endif
               const real sv = sx_l[kc] * orx + sy_l[kc] * ory;
               const bool ok = !((sv < (real)0) | (sv > p.range) | (od2 - sv * sv > p.r_p2));
               bO[kc] = ok ? sv : INF;
             }
           }
-#if !MADRL_WW_DEFERRED_TAIL
-          unsigned hitE = 0u, hitP = 0u;
-#endif
           if constexpr (SMEM) {
             constexpr uint32_t S = CandSlot<real>::kStride;
             uint32_t endU = slots, nEc = 0u, nPc = 0u, top = slots;
@@ -357,11 +282,6 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
               const unsigned cm = __ballot_sync(FULL_MASK, near);
               const bool hit = d2 <= coll2_l[c];
               if (hit) col[c] |= 1u << pi;
-#if !MADRL_WW_DEFERRED_TAIL
-              const unsigned hb = __ballot_sync(FULL_MASK, hit);
-              hitE |= hb & mE[c];
-              hitP |= hb & mP[c];
-#endif
               // slot = rank among the candidates in ascending object index (= lane + 32 c)
               if (near) CandSlot<real>::put(top + (uint32_t)__popc(cm & ((1u << lane) - 1u)) * S, rx, ry, d2, vx[c], vy[c]);
               if (c == 0) endU = slots + (uint32_t)__popc(cm & mU[0]) * S;   // pursuers live in chunk 0 (Np <= 32)
@@ -377,7 +297,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
 #pragma unroll
             for (int kc = 0; kc < KCH; ++kc) { bE[kc] = bP[kc] = bU[kc] = up; aE[kc] = aP[kc] = aU[kc] = slots; }
 #define MADRL_WW_SCAN(A0, A1, BEST, AT)                                                  \
-  MADRL_PRAGMA(unroll MADRL_WW_SMEM_UNROLL)                                              \
+  _Pragma("unroll 2")                                                                  \
   for (uint32_t a = (A0); a != (A1); a += S) {                                           \
     real jx, jy, jd;                                                                     \
     CandSlot<real>::geom(a, jx, jy, jd);                                                 \
@@ -423,9 +343,6 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
             }
             __syncwarp();   // the next pursuer's staging overwrites the slots
           } else {
-#if MADRL_WW_LEAN_SENSE
-          unsigned candU = 0u, candE = 0u, candP = 0u;   // warp-uniform: in-range candidates per class
-#endif
 #pragma unroll
           for (int c = 0; c < OPL; ++c) {
             // lanes as OBJECTS: geometry, collisions (ww:278-293), conservative range cull
@@ -433,39 +350,9 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
             const real d2 = rx * rx + ry * ry;
             unsigned cm = __ballot_sync(FULL_MASK, d2 <= cull2_l[c]);
             if (c == 0) cm &= ~(1u << pi);  // ww:70-71 `same`
-#if MADRL_WW_LEAN_SENSE
-            candU |= cm & mU[c]; candE |= cm & mE[c]; candP |= cm & mP[c];
-#endif
             const bool hit = d2 <= coll2_l[c];
             if (hit) col[c] |= 1u << pi;
-#if !MADRL_WW_DEFERRED_TAIL
-            const unsigned hb = __ballot_sync(FULL_MASK, hit);
-            hitE |= hb & mE[c];
-            hitP |= hb & mP[c];
-#endif
             // lanes as SENSORS: scan the surviving candidates of this chunk, ascending index
-#if MADRL_WW_MERGED_SCAN
-            // one loop over all candidates; the class of candidate j is warp-uniform
-            for (unsigned m = cm; m != 0u; m &= m - 1u) {
-              const int j = __ffs(m) - 1;
-              const real jx = __shfl_sync(FULL_MASK, rx, j), jy = __shfl_sync(FULL_MASK, ry, j);
-#if MADRL_WW_NO_JD_SHFL
-              const real jd = jx * jx + jy * jy;
-#else
-              const real jd = __shfl_sync(FULL_MASK, d2, j);
-#endif
-              const int idx = j + 32 * c;
-              const unsigned bit = 1u << j;
-#pragma unroll
-              for (int kc = 0; kc < KCH; ++kc) {
-                const real sv = sx_l[kc] * jx + sy_l[kc] * jy;
-                const bool ok = !((sv < (real)0) | (sv > p.range) | (jd - sv * sv > p.r_p2));
-                if (bit & mE[c])      { if (ok && sv < bE[kc]) { bE[kc] = sv; iE[kc] = idx; } }
-                else if (bit & mP[c]) { if (ok && sv < bP[kc]) { bP[kc] = sv; iP[kc] = idx; } }
-                else                  { if (ok && sv < bU[kc]) { bU[kc] = sv; iU[kc] = idx; } }
-              }
-            }
-#else
 #pragma unroll
             for (int kc = 0; kc < KCH; ++kc) {
               const real sx = sx_l[kc], sy = sy_l[kc];
@@ -483,46 +370,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
               MADRL_WW_SCAN(mP[c], bP[kc], iP[kc])
 #undef MADRL_WW_SCAN
             }
-#endif
           }
-#if MADRL_WW_LEAN_SENSE
-#pragma unroll
-          for (int kc = 0; kc < KCH; ++kc) {
-            const real sx = sx_l[kc], sy = sy_l[kc];
-            // features ww:312-353, 388-395: feature-major, sensor-minor
-            const int k = lane + 32 * kc;
-            const real z = (real)0;
-            real* o = obs_row + 32 * kc;   // this lane's column
-            real fE = z, sE = z, fP = z, sP = z, fU = z, sU = z;
-#define MADRL_WW_CLASS(CAND, BEST, IDX, F, S)                                                     \
-  if ((CAND) != 0u) {                                                                              \
-    const bool h = BEST[kc] < INF;                                                                 \
-    F = h ? BEST[kc] : z;                                                                          \
-    if (p.speed_features) {                                                                        \
-      real ox = z, oy = z;                                                                         \
-      _Pragma("unroll") for (int c = 0; c < OPL; ++c) {                                            \
-        const real cx_ = __shfl_sync(FULL_MASK, vx[c], IDX[kc] & 31), cy_ = __shfl_sync(FULL_MASK, vy[c], IDX[kc] & 31); \
-        if (OPL == 1 || (IDX[kc] >> 5) == c) { ox = cx_; oy = cy_; }                               \
-      }                                                                                            \
-      S = h ? sx * (ox - mvx) + sy * (oy - mvy) : z;                                               \
-    }                                                                                              \
-  }
-            MADRL_WW_CLASS(candE, bE, iE, fE, sE)
-            MADRL_WW_CLASS(candP, bP, iP, fP, sP)
-            MADRL_WW_CLASS(candU, bU, iU, fU, sU)
-#undef MADRL_WW_CLASS
-            if (k < K) {
-              store_stream(o + 0 * K, bO[kc] < INF ? bO[kc] : z);
-              if (p.speed_features) {
-                store_stream(o + 1 * K, fE); store_stream(o + 2 * K, sE);
-                store_stream(o + 3 * K, fP); store_stream(o + 4 * K, sP);
-                store_stream(o + 5 * K, fU); store_stream(o + 6 * K, sU);
-              } else {
-                store_stream(o + 1 * K, fE); store_stream(o + 2 * K, fP); store_stream(o + 3 * K, fU);
-              }
-            }
-          }
-#else
 #pragma unroll
           for (int kc = 0; kc < KCH; ++kc) {
             const real sx = sx_l[kc], sy = sy_l[kc];
@@ -565,27 +413,11 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
               store_stream(o + 3 * K, hU ? bU[kc] : z);
             }
           }
-#endif
           }
-#if !MADRL_WW_DEFERRED_TAIL
-          // ww:411-428 tail: collided-with-evader, collided-with-poison, id -- one branch-free store
-          if (lane < n_tail) {
-            const unsigned bits = (hitE ? 1u : 0u) | (hitP ? 2u : 0u);
-            const real tv = lane < 2 ? (real)((bits >> lane) & 1u) : (real)(pi + 1);
-            store_stream(obs_row + n_feat * K, tv);
-          }
-#endif
         }
         // ---- catches, respawn, rewards: ww:285,293,358-385 -----------------------------------------
         unsigned whoE = 0u, whoP = 0u, whoEnc = 0u;
         int nE = 0, nP = 0, nEnc = 0;
-#if MADRL_WW_SKIP_EMPTY_CATCH
-        // most steps nobody touches anything: one ballot decides whether the catch logic runs at all
-        bool touched = false;
-#pragma unroll
-        for (int c = 0; c < OPL; ++c) touched |= col[c] != 0u;
-        if (__ballot_sync(FULL_MASK, touched) != 0u) {
-#endif
 #pragma unroll
         for (int c = 0; c < OPL; ++c) {
           const int cnt = __popc(col[c]);
@@ -612,10 +444,6 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
         whoE = __reduce_or_sync(FULL_MASK, whoE);
         whoP = __reduce_or_sync(FULL_MASK, whoP);
         whoEnc = __reduce_or_sync(FULL_MASK, whoEnc);
-#if MADRL_WW_SKIP_EMPTY_CATCH
-        }
-#endif
-#if MADRL_WW_DEFERRED_TAIL
         // ww:411-428 tail of every pursuer's row: [touched an evader, touched a poison, id]; lane i
         // writes pursuer i's.  whoEnc / whoP are exactly the any-collision masks (ww:376, ww:293).
         if (lane < p.Np) {
@@ -624,7 +452,6 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
           store_stream(tp + 1, (real)((whoP >> lane) & 1u));
           if (p.addid) store_stream(tp + 2, (real)(lane + 1));
         }
-#endif
         if (!pass && lane < p.Np) {
           real r = pen;
           if (p.reward_global) {
@@ -875,23 +702,18 @@ static real exact_sq_threshold(double thr_d) {
 
 template <typename real, int OPL, int KCH, int KC, bool PEER>
 static int ww_launch_inst2(madrl_ww* h, const WWParams<real>& p, cudaStream_t stream) {
-#if MADRL_WW_ONE_WARP_BLOCKS
-  const int wpb = 1;
-#else
-  const int wpb = h->warps_per_block > 0 ? h->warps_per_block : 4;
-#endif
   const auto kfn = ww_kernel<real, OPL, KCH, KC, PEER>;
   int resident = 0;
-  const size_t smem = OPL >= MADRL_WW_SMEM_MIN_OPL ? (size_t)wpb * p.Nall * CandSlot<real>::kStride : 0;
+  const size_t smem = OPL >= 2 ? (size_t)p.Nall * CandSlot<real>::kStride : 0;   // candidate slots
   if (smem > 48 * 1024)
     MADRL_CUDA_CHECK(cudaFuncSetAttribute(kfn,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, wpb * 32, smem));
+  MADRL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, 32, smem));
   if (resident < 1) resident = 1;
   if (h->blocks_per_sm > 0 && h->blocks_per_sm < resident) resident = h->blocks_per_sm;
-  int grid = (p.E + wpb - 1) / wpb;                  // one warp per env ...
+  int grid = p.E;                                    // one warp (= one 32-thread block) per env ...
   if (grid > h->sms * resident) grid = h->sms * resident;  // ... or a single persistent wave
-  MADRL_LAUNCH(kfn, grid, wpb * 32, smem, stream, p);
+  MADRL_LAUNCH(kfn, grid, 32, smem, stream, p);
   g_launches.fetch_add(1);
   MADRL_CUDA_CHECK(cudaGetLastError());
   return MADRL_OK;
