@@ -50,8 +50,13 @@ extern "C" {
 
 const char* madrl_last_error(void);
 int madrl_version(void);
+/* sizeof(madrl_{ww,pursuit,hostage}_{config,layout}) as this library was compiled: a foreign-language
+ * binding compares them with its own struct definitions before the first call. */
+void madrl_abi_sizes(int32_t* out6);
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 uint64_t madrl_launch_count(void);
+/* Device->host bytes per pipeline chunk of the `*_rollout_host` entry points (0 = default 32 MB). */
+void madrl_set_host_chunk_bytes(size_t bytes);
 
 /* CUDA-IPC buffers for the fused multi-GPU exchange (see madrl_ww_set_peers): allocate + export on
  * the owning rank, open on every other rank with ITS device current (peer access over NVLink is
@@ -60,6 +65,19 @@ int madrl_ipc_alloc(size_t bytes, void** ptr, unsigned char* handle64);
 int madrl_ipc_open(const unsigned char* handle64, void** ptr);
 int madrl_ipc_close(void* ptr);
 int madrl_ipc_free(void* ptr);
+
+/* Stream-ordered primitives of the per-rollout multi-GPU exchange (madrl_b200/dist.py
+ * AsyncRootGather): executed by the copy engines / the stream front end, no SM involved, so the
+ * persistent rollout kernel of the next rollout is not disturbed.  The reference's counterpart is
+ * the workers' pickled path return to the master (rllab/rllab/sampler/stateful_pool.py:102-157).
+ *   madrl_copy_async          device->device copy; either side may be a CUDA-IPC peer mapping (NVLink)
+ *   madrl_stream_write32      *addr = value when the stream reaches this point (LOCAL device memory)
+ *   madrl_stream_wait_geq32   the stream waits until (int32)(*addr - value) >= 0 (LOCAL device memory)
+ *   madrl_stream_memops_available   1 if the driver exports the two stream memory operations */
+int madrl_stream_memops_available(void);
+int madrl_copy_async(void* dst_dev, const void* src_dev, size_t bytes, void* stream);
+int madrl_stream_write32(void* stream, void* addr_dev, uint32_t value);
+int madrl_stream_wait_geq32(void* stream, void* addr_dev, uint32_t value);
 
 /* ------------------------------------------------------------------ MAWaterWorld ------------ */
 typedef struct madrl_ww_config {
@@ -117,7 +135,8 @@ int madrl_ww_set_peers(madrl_ww* h, int n_dest, int slot, int t_max, void* const
  * reference's internal step(zeros); obs_dev real [E][Np][obs_dim], rows of unmasked envs untouched. */
 int madrl_ww_reset(madrl_ww* h, const uint8_t* mask_dev, void* obs_dev, void* stream);
 /* T lockstep steps in ONE launch.  actions_dev real [T][E][Np][2]; obs_dev real [T][E][Np][obs_dim];
- * rew_dev real [T][E][Np]; done_dev uint8 [T][E]; info_dev int32 [T][E][2] = (evcatches, pocatches).
+ * rew_dev real [T][E][Np]; done_dev uint8 [T][E]; info_dev int32 [T][E][2] = (evcatches, pocatches),
+ * 8-byte aligned (a row is one 8-byte store).
  * auto_reset != 0: VecEnvExecutor.step semantics -- a done env is reset in place and the obs
  * slot of that step holds the reset observation. */
 int madrl_ww_rollout(madrl_ww* h, int T, const void* actions_dev, void* obs_dev, void* rew_dev,
@@ -126,10 +145,20 @@ int madrl_ww_rollout(madrl_ww* h, int T, const void* actions_dev, void* obs_dev,
 int madrl_ww_step(madrl_ww* h, const void* actions_dev, void* obs_dev, void* rew_dev,
                   uint8_t* done_dev, int32_t* info_dev, int auto_reset, void* stream);
 /* Host-buffer variants (what a non-torch FFI caller binds): copies are part of the call and the
- * call returns after the results are in the host buffers. */
+ * call returns after the results are in the host buffers (pinned memory for full PCIe speed).  The
+ * rollout is chunked: the copy engines drain chunk c while chunk c+1 is computed.  They run on two
+ * internal streams that are ordered after earlier work on the legacy default stream; work the caller
+ * queued on other streams must be synchronised by the caller.
+ * `_host2` takes flags: MADRL_HOST_OBS_LAST = only the LAST step's observations come back (obs_host is
+ * then [E][Np][D]) -- the policy-on-device mode: rewards / dones / infos of every step + the
+ * observation needed to continue; the call then runs at the kernel's rate instead of PCIe's. */
+#define MADRL_HOST_OBS_LAST 1
 int madrl_ww_reset_host(madrl_ww* h, const uint8_t* mask_host, void* obs_host);
 int madrl_ww_rollout_host(madrl_ww* h, int T, const void* actions_host, void* obs_host,
                           void* rew_host, uint8_t* done_host, int32_t* info_host, int auto_reset);
+int madrl_ww_rollout_host2(madrl_ww* h, int T, const void* actions_host, void* obs_host,
+                           void* rew_host, uint8_t* done_host, int32_t* info_host, int auto_reset,
+                           int flags);
 
 /* ------------------------------------------------------------------ PursuitEvade ------------ */
 typedef struct madrl_pursuit_config {
@@ -188,6 +217,9 @@ int madrl_pursuit_reset_host(madrl_pursuit* h, const uint8_t* mask_host, float* 
 int madrl_pursuit_rollout_host(madrl_pursuit* h, int T, const int32_t* actions_host, float* obs_host,
                                float* rew_host, uint8_t* done_host, int32_t* info_host,
                                int auto_reset);
+int madrl_pursuit_rollout_host2(madrl_pursuit* h, int T, const int32_t* actions_host, float* obs_host,
+                                float* rew_host, uint8_t* done_host, int32_t* info_host,
+                                int auto_reset, int flags);
 
 /* ------------------------------------------------------------------ ContinuousHostageWorld -- */
 typedef struct madrl_hostage_config {
@@ -224,7 +256,8 @@ int madrl_hostage_set_launch(madrl_hostage* h, int warps_per_block, int blocks_p
 /* obs_dev real [E][n_good][obs_dim] */
 int madrl_hostage_reset(madrl_hostage* h, const uint8_t* mask_dev, void* obs_dev, void* stream);
 /* actions_dev real [T][E][n_good][2]; obs_dev real [T][E][n_good][obs_dim]; rew_dev real
- * [T][E][n_good]; done_dev uint8 [T][E]; info_dev int32 [T][E][2] = (ho_saved, cr_encs). */
+ * [T][E][n_good]; done_dev uint8 [T][E]; info_dev int32 [T][E][2] = (ho_saved, cr_encs), 8-byte
+ * aligned (a row is one 8-byte store). */
 int madrl_hostage_rollout(madrl_hostage* h, int T, const void* actions_dev, void* obs_dev,
                           void* rew_dev, uint8_t* done_dev, int32_t* info_dev, int auto_reset,
                           void* stream);
@@ -234,6 +267,9 @@ int madrl_hostage_reset_host(madrl_hostage* h, const uint8_t* mask_host, void* o
 int madrl_hostage_rollout_host(madrl_hostage* h, int T, const void* actions_host, void* obs_host,
                                void* rew_host, uint8_t* done_host, int32_t* info_host,
                                int auto_reset);
+int madrl_hostage_rollout_host2(madrl_hostage* h, int T, const void* actions_host, void* obs_host,
+                                void* rew_host, uint8_t* done_host, int32_t* info_host,
+                                int auto_reset, int flags);
 
 /* ------------------------------------------------------------------ trajectory post-processing
  * (SURVEY.md 8f rows 2-3).  All tensors are device pointers, float32 unless noted, time-major. */

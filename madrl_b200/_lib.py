@@ -89,11 +89,19 @@ def _declare(lib):
     vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
     lib.madrl_last_error.restype = C.c_char_p
     lib.madrl_version.restype = C.c_int
+    lib.madrl_abi_sizes.argtypes = [C.POINTER(C.c_int32)]
+    lib.madrl_abi_sizes.restype = None
     lib.madrl_launch_count.restype = C.c_uint64
+    lib.madrl_set_host_chunk_bytes.argtypes = [C.c_size_t]
+    lib.madrl_set_host_chunk_bytes.restype = None
     lib.madrl_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
     lib.madrl_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     lib.madrl_ipc_close.argtypes = [vp]
     lib.madrl_ipc_free.argtypes = [vp]
+    lib.madrl_stream_memops_available.restype = C.c_int
+    lib.madrl_copy_async.argtypes = [vp, vp, C.c_size_t, vp]
+    lib.madrl_stream_write32.argtypes = [vp, vp, C.c_uint32]
+    lib.madrl_stream_wait_geq32.argtypes = [vp, vp, C.c_uint32]
     lib.madrl_ww_state_layout.argtypes = [C.POINTER(WWConfig), C.POINTER(WWLayout)]
     lib.madrl_ww_create.argtypes = [C.POINTER(WWConfig), vp, C.POINTER(vp)]
     lib.madrl_ww_destroy.argtypes = [vp]
@@ -107,6 +115,7 @@ def _declare(lib):
     lib.madrl_ww_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
     lib.madrl_ww_reset_host.argtypes = [vp, vp, vp]
     lib.madrl_ww_rollout_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
+    lib.madrl_ww_rollout_host2.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32]
     lib.madrl_gae_f32.argtypes = [i32, i32, i32, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp]
     lib.madrl_frame_stack_f32.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.madrl_standardize_f32.argtypes = [i32, C.c_size_t, vp, vp, vp, C.c_double, C.c_double, i32,
@@ -126,6 +135,7 @@ def _declare(lib):
     lib.madrl_hostage_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
     lib.madrl_hostage_reset_host.argtypes = [vp, vp, vp]
     lib.madrl_hostage_rollout_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
+    lib.madrl_hostage_rollout_host2.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32]
     lib.madrl_pursuit_state_layout.argtypes = [C.POINTER(PEConfig), C.POINTER(PELayout)]
     lib.madrl_pursuit_create.argtypes = [C.POINTER(PEConfig), vp, vp, C.POINTER(vp)]
     lib.madrl_pursuit_destroy.argtypes = [vp]
@@ -139,24 +149,55 @@ def _declare(lib):
     lib.madrl_pursuit_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
     lib.madrl_pursuit_reset_host.argtypes = [vp, vp, vp]
     lib.madrl_pursuit_rollout_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
+    lib.madrl_pursuit_rollout_host2.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32]
 
 
 def lib():
     """Load (building if needed) the CUDA library.  Raises EngineError on failure."""
     global _lib
     if _lib is None:
-        path = os.environ.get("MADRL_B200_LIB", _build.LIB)   # override: kernel-variant experiments
-        if not os.path.exists(path) or os.environ.get("MADRL_B200_REBUILD"):
+        path = os.environ.get("MADRL_B200_LIB")            # override: kernel-variant experiments
+        if path is None:
+            # build() is a no-op when the library was built from exactly the sources in the tree
+            # (content hash); a stale git-ignored .so left over from other sources is rebuilt, not loaded
             try:
-                path = _build.build()
+                path = _build.build(force=bool(os.environ.get("MADRL_B200_REBUILD")))
             except Exception as e:  # no nvcc / compile error: there is no CPU fallback
-                raise EngineError("madrl_b200 CUDA library is missing and could not be built: %s" % e)
+                raise EngineError("madrl_b200 CUDA library is missing or stale and could not be built: %s" % e)
         try:
-            _lib = C.CDLL(path)
+            lib_ = C.CDLL(path)
         except OSError as e:
             raise EngineError("cannot load %s: %s" % (path, e))
-        _declare(_lib)
+        _declare(lib_)
+        sizes = (C.c_int32 * 6)()
+        lib_.madrl_abi_sizes(sizes)
+        want = [C.sizeof(t) for t in (WWConfig, WWLayout, PEConfig, PELayout, HWConfig, HWLayout)]
+        if list(sizes) != want:
+            raise EngineError("%s was built against another include/madrl_b200.h: struct sizes %s, this "
+                              "binding expects %s" % (path, list(sizes), want))
+        _lib = lib_
     return _lib
+
+
+def require_tensor(t, name, dtype, shape, device):
+    """Validate a caller-supplied tensor before its data_ptr() crosses the C ABI (a wrong dtype,
+    a non-contiguous view or a short buffer would otherwise be silent garbage or an out-of-bounds
+    device write).  `device`: a torch.device for device buffers, 'cpu' for host buffers."""
+    import torch
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor, got %r" % (name, type(t)))
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    if device == 'cpu':
+        if t.device.type != 'cpu':
+            raise ValueError("%s must be a host tensor, got %s" % (name, t.device))
+    elif t.device != device:
+        raise ValueError("%s must live on %s, got %s" % (name, device, t.device))
+    return t
 
 
 def check(rc):

@@ -21,13 +21,26 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def source_hash():
+    """sha256 over every source / header the library is built from + the nvcc flags.  A content
+    hash, not mtimes: the tree is copied to the GPU box and git checkouts do not keep mtimes."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    deps = sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(
+        glob.glob(os.path.join(HERE, "..", "include", "*.h")))
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale():
-    if not os.path.exists(LIB):
+    """True if the library is missing or was built from other sources than the ones in the tree."""
+    if not os.path.exists(LIB) or not os.path.exists(LIB + ".srchash"):
         return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(
-        os.path.join(HERE, "..", "include", "*.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(LIB + ".srchash") as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -58,6 +71,8 @@ def build(force=False, verbose=False):
     if res.returncode != 0:
         sys.stderr.write(res.stdout)
         raise RuntimeError("nvcc link failed (%d): %s" % (res.returncode, " ".join(cmd)))
+    with open(LIB + ".srchash", "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 

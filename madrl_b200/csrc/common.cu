@@ -8,6 +8,7 @@ namespace madrl {
 
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+std::atomic<size_t> g_host_chunk_bytes{(size_t)32 << 20};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -29,8 +30,15 @@ int sm_count(int device) {
 }  // namespace madrl
 
 extern "C" const char* madrl_last_error(void) { return madrl::g_err; }
-extern "C" int madrl_version(void) { return 100; }
+extern "C" int madrl_version(void) { return 200; }
+// sizeof of every struct that crosses the ABI: a binding built against another header refuses to run
+extern "C" void madrl_abi_sizes(int32_t* out6) {
+  out6[0] = (int32_t)sizeof(madrl_ww_config); out6[1] = (int32_t)sizeof(madrl_ww_layout);
+  out6[2] = (int32_t)sizeof(madrl_pursuit_config); out6[3] = (int32_t)sizeof(madrl_pursuit_layout);
+  out6[4] = (int32_t)sizeof(madrl_hostage_config); out6[5] = (int32_t)sizeof(madrl_hostage_layout);
+}
 extern "C" uint64_t madrl_launch_count(void) { return madrl::g_launches.load(); }
+extern "C" void madrl_set_host_chunk_bytes(size_t bytes) { madrl::g_host_chunk_bytes.store(bytes ? bytes : ((size_t)32 << 20)); }
 
 // ---- CUDA IPC helpers for the fused multi-GPU exchange (madrl_b200/dist.py PeerGather) -----------
 // Buffers are cudaMalloc'ed here (not sub-allocated by a framework allocator) so that the IPC

@@ -11,6 +11,7 @@ namespace madrl {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
+extern std::atomic<size_t> g_host_chunk_bytes;   // device->host bytes per chunk of the host-buffer rollouts
 int sm_count(int device);
 
 #define MADRL_CUDA_CHECK(expr)                                                          \

@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "philox.cuh"
+#include "host_pipeline.cuh"
 
 namespace madrl {
 
@@ -423,8 +424,7 @@ struct madrl_pursuit {
   bool owns_state;
   int device, sms;
   int warps_per_block, blocks_per_sm;
-  void* stage;
-  size_t stage_bytes;
+  madrl::HostPipe pipe;   // staging + streams of the host-buffer entry points (lazily created)
 };
 
 static int pe_validate(const madrl_pursuit_config* c) {
@@ -473,7 +473,7 @@ extern "C" int madrl_pursuit_create(const madrl_pursuit_config* c, const int32_t
   if (rc) return rc;
   madrl_pursuit* h = new (std::nothrow) madrl_pursuit();
   if (!h) return MADRL_ENOMEM;
-  h->cfg = *c; h->lay = lay; h->stage = nullptr; h->stage_bytes = 0;
+  h->cfg = *c; h->lay = lay;
   h->warps_per_block = 0; h->blocks_per_sm = 0;
   cudaError_t e = cudaGetDevice(&h->device);
   if (e != cudaSuccess) { set_error("cudaGetDevice: %s", cudaGetErrorString(e)); delete h; return MADRL_ECUDA; }
@@ -508,7 +508,7 @@ extern "C" int madrl_pursuit_create(const madrl_pursuit_config* c, const int32_t
 extern "C" int madrl_pursuit_destroy(madrl_pursuit* h) {
   if (!h) return MADRL_OK;
   if (h->owns_state && h->state) cudaFree(h->state);
-  if (h->stage) cudaFree(h->stage);
+  h->pipe.destroy();
   delete h;
   return MADRL_OK;
 }
@@ -613,23 +613,13 @@ extern "C" int madrl_pursuit_step(madrl_pursuit* h, const int32_t* actions_dev, 
   return madrl_pursuit_rollout(h, 1, actions_dev, obs_dev, rew_dev, done_dev, info_dev, auto_reset, stream);
 }
 
-static int pe_stage(madrl_pursuit* h, size_t bytes) {
-  if (h->stage_bytes >= bytes) return MADRL_OK;
-  if (h->stage) cudaFree(h->stage);
-  h->stage = nullptr; h->stage_bytes = 0;
-  cudaError_t e = cudaMalloc(&h->stage, bytes);
-  if (e != cudaSuccess) { set_error("cudaMalloc(stage %zu): %s", bytes, cudaGetErrorString(e)); return MADRL_ENOMEM; }
-  h->stage_bytes = bytes;
-  return MADRL_OK;
-}
-
 extern "C" int madrl_pursuit_reset_host(madrl_pursuit* h, const uint8_t* mask_host, float* obs_host) {
   MADRL_REQUIRE(h != nullptr && obs_host != nullptr, "handle/obs is NULL");
   const size_t E = h->cfg.n_envs;
   const size_t obs_b = E * h->cfg.n_pursuers * h->lay.obs_dim * 4, mask_off = align_up(obs_b, 256);
-  int rc = pe_stage(h, mask_off + E);
+  int rc = h->pipe.ensure(mask_off + E);
   if (rc) return rc;
-  char* st = (char*)h->stage;
+  char* st = (char*)h->pipe.stage;
   uint8_t* mask_dev = nullptr;
   if (mask_host) {
     mask_dev = (uint8_t*)(st + mask_off);
@@ -643,27 +633,24 @@ extern "C" int madrl_pursuit_reset_host(madrl_pursuit* h, const uint8_t* mask_ho
   return MADRL_OK;
 }
 
-extern "C" int madrl_pursuit_rollout_host(madrl_pursuit* h, int T, const int32_t* actions_host, float* obs_host,
-                                          float* rew_host, uint8_t* done_host, int32_t* info_host, int auto_reset) {
+extern "C" int madrl_pursuit_rollout_host2(madrl_pursuit* h, int T, const int32_t* actions_host, float* obs_host,
+                                           float* rew_host, uint8_t* done_host, int32_t* info_host, int auto_reset,
+                                           int flags) {
   MADRL_REQUIRE(h != nullptr, "handle is NULL");
   MADRL_REQUIRE(T >= 1, "T must be >= 1");
   MADRL_REQUIRE(actions_host && obs_host && rew_host && done_host && info_host, "NULL trajectory buffer");
-  const size_t E = h->cfg.n_envs, Np = h->cfg.n_pursuers, TT = (size_t)T;
-  const size_t act_b = TT * E * Np * 4, obs_b = TT * E * Np * h->lay.obs_dim * 4, rew_b = TT * E * Np * 4;
-  const size_t done_b = TT * E, info_b = TT * E * 4;
-  const size_t o_obs = align_up(act_b, 256), o_rew = align_up(o_obs + obs_b, 256);
-  const size_t o_done = align_up(o_rew + rew_b, 256), o_info = align_up(o_done + done_b, 256);
-  int rc = pe_stage(h, o_info + info_b);
-  if (rc) return rc;
-  char* st = (char*)h->stage;
-  MADRL_CUDA_CHECK(cudaMemcpyAsync(st, actions_host, act_b, cudaMemcpyHostToDevice, 0));
-  rc = madrl_pursuit_rollout(h, T, (const int32_t*)st, (float*)(st + o_obs), (float*)(st + o_rew),
-                             (uint8_t*)(st + o_done), (int32_t*)(st + o_info), auto_reset, nullptr);
-  if (rc) return rc;
-  MADRL_CUDA_CHECK(cudaMemcpyAsync(obs_host, st + o_obs, obs_b, cudaMemcpyDeviceToHost, 0));
-  MADRL_CUDA_CHECK(cudaMemcpyAsync(rew_host, st + o_rew, rew_b, cudaMemcpyDeviceToHost, 0));
-  MADRL_CUDA_CHECK(cudaMemcpyAsync(done_host, st + o_done, done_b, cudaMemcpyDeviceToHost, 0));
-  MADRL_CUDA_CHECK(cudaMemcpyAsync(info_host, st + o_info, info_b, cudaMemcpyDeviceToHost, 0));
-  MADRL_CUDA_CHECK(cudaStreamSynchronize(0));
-  return MADRL_OK;
+  MADRL_REQUIRE((flags & ~MADRL_HOST_OBS_LAST) == 0, "unknown flags %d", flags);
+  const size_t E = h->cfg.n_envs, Np = h->cfg.n_pursuers;
+  const StepBytes sb = {E * Np * 4, E * Np * h->lay.obs_dim * 4, E * Np * 4, E, E * 4};
+  return host_rollout(h->pipe, T, sb, actions_host, obs_host, rew_host, done_host, info_host,
+                      flags & MADRL_HOST_OBS_LAST,
+                      [&](int, int Tc, char* a, char* o, char* r, char* d, char* i, cudaStream_t st) {
+                        return madrl_pursuit_rollout(h, Tc, (const int32_t*)a, (float*)o, (float*)r, (uint8_t*)d,
+                                                     (int32_t*)i, auto_reset, st);
+                      });
+}
+
+extern "C" int madrl_pursuit_rollout_host(madrl_pursuit* h, int T, const int32_t* actions_host, float* obs_host,
+                                          float* rew_host, uint8_t* done_host, int32_t* info_host, int auto_reset) {
+  return madrl_pursuit_rollout_host2(h, T, actions_host, obs_host, rew_host, done_host, info_host, auto_reset, 0);
 }

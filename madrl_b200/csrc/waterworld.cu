@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "philox.cuh"
+#include "host_pipeline.cuh"
 
 namespace madrl {
 
@@ -548,9 +549,7 @@ struct madrl_ww {
   bool owns_state;
   int device, sms;
   int warps_per_block, blocks_per_sm;
-  // staging for the host-buffer entry points (lazily sized)
-  void* stage;
-  size_t stage_bytes;
+  madrl::HostPipe pipe;   // staging + streams of the host-buffer entry points (lazily created)
   // peer gather buffers (multi-GPU fused exchange); n_peers == 0: disabled
   int n_peers, peer_rank, peer_tmax;
   void* peer_rew[8];
@@ -621,8 +620,6 @@ extern "C" int madrl_ww_create(const madrl_ww_config* c, void* state_dev, madrl_
   if (!h) return MADRL_ENOMEM;
   h->cfg = *c;
   h->lay = lay;
-  h->stage = nullptr;
-  h->stage_bytes = 0;
   h->warps_per_block = 0;
   h->blocks_per_sm = 0;
   h->n_peers = 0; h->peer_rank = 0; h->peer_tmax = 0;
@@ -649,7 +646,7 @@ extern "C" int madrl_ww_create(const madrl_ww_config* c, void* state_dev, madrl_
 extern "C" int madrl_ww_destroy(madrl_ww* h) {
   if (!h) return MADRL_OK;
   if (h->owns_state && h->state) cudaFree(h->state);
-  if (h->stage) cudaFree(h->stage);
+  h->pipe.destroy();
   delete h;
   return MADRL_OK;
 }
@@ -673,6 +670,7 @@ extern "C" int madrl_ww_set_peers(madrl_ww* h, int n_peers, int rank, int t_max,
   MADRL_REQUIRE(rew_peers && done_peers && info_peers, "NULL peer pointer table");
   for (int d = 0; d < n_peers; ++d) {
     MADRL_REQUIRE(rew_peers[d] && done_peers[d] && info_peers[d], "NULL peer buffer %d", d);
+    MADRL_REQUIRE(((uintptr_t)info_peers[d] & 7) == 0, "peer info buffer %d must be 8-byte aligned", d);
     h->peer_rew[d] = rew_peers[d]; h->peer_done[d] = done_peers[d]; h->peer_info[d] = info_peers[d];
   }
   h->n_peers = n_peers; h->peer_rank = rank; h->peer_tmax = t_max;
@@ -813,6 +811,7 @@ extern "C" int madrl_ww_rollout(madrl_ww* h, int T, const void* actions_dev, voi
   MADRL_REQUIRE(h != nullptr, "handle is NULL");
   MADRL_REQUIRE(T >= 1, "T must be >= 1");
   MADRL_REQUIRE(actions_dev && obs_dev && rew_dev && done_dev && info_dev, "NULL trajectory buffer");
+  MADRL_REQUIRE(((uintptr_t)info_dev & 7) == 0, "info_dev must be 8-byte aligned (rows are stored as one 8-byte word)");
   return h->cfg.fp64 ? ww_launch<double>(h, 0, T, actions_dev, obs_dev, rew_dev, done_dev, info_dev, nullptr, auto_reset, (cudaStream_t)stream)
                      : ww_launch<float>(h, 0, T, actions_dev, obs_dev, rew_dev, done_dev, info_dev, nullptr, auto_reset, (cudaStream_t)stream);
 }
@@ -823,25 +822,14 @@ extern "C" int madrl_ww_step(madrl_ww* h, const void* actions_dev, void* obs_dev
 }
 
 // ---- host-buffer entry points -------------------------------------------------------------------
-static int ww_stage(madrl_ww* h, size_t bytes) {
-  if (h->stage_bytes >= bytes) return MADRL_OK;
-  if (h->stage) cudaFree(h->stage);
-  h->stage = nullptr;
-  h->stage_bytes = 0;
-  cudaError_t e = cudaMalloc(&h->stage, bytes);
-  if (e != cudaSuccess) { set_error("cudaMalloc(stage %zu): %s", bytes, cudaGetErrorString(e)); return MADRL_ENOMEM; }
-  h->stage_bytes = bytes;
-  return MADRL_OK;
-}
-
 extern "C" int madrl_ww_reset_host(madrl_ww* h, const uint8_t* mask_host, void* obs_host) {
   MADRL_REQUIRE(h != nullptr && obs_host != nullptr, "handle/obs is NULL");
   const size_t E = h->cfg.n_envs, rb = h->lay.real_bytes;
   const size_t obs_b = E * h->cfg.n_pursuers * h->lay.obs_dim * rb;
   const size_t mask_off = align_up(obs_b, 256);
-  int rc = ww_stage(h, mask_off + E);
+  int rc = h->pipe.ensure(mask_off + E);
   if (rc) return rc;
-  char* st = (char*)h->stage;
+  char* st = (char*)h->pipe.stage;
   uint8_t* mask_dev = nullptr;
   if (mask_host) {
     mask_dev = (uint8_t*)(st + mask_off);
@@ -856,28 +844,24 @@ extern "C" int madrl_ww_reset_host(madrl_ww* h, const uint8_t* mask_host, void* 
   return MADRL_OK;
 }
 
-extern "C" int madrl_ww_rollout_host(madrl_ww* h, int T, const void* actions_host, void* obs_host,
-                                     void* rew_host, uint8_t* done_host, int32_t* info_host,
-                                     int auto_reset) {
+extern "C" int madrl_ww_rollout_host2(madrl_ww* h, int T, const void* actions_host, void* obs_host,
+                                      void* rew_host, uint8_t* done_host, int32_t* info_host,
+                                      int auto_reset, int flags) {
   MADRL_REQUIRE(h != nullptr, "handle is NULL");
   MADRL_REQUIRE(T >= 1, "T must be >= 1");
   MADRL_REQUIRE(actions_host && obs_host && rew_host && done_host && info_host, "NULL trajectory buffer");
-  const size_t E = h->cfg.n_envs, Np = h->cfg.n_pursuers, rb = h->lay.real_bytes, TT = (size_t)T;
-  const size_t act_b = TT * E * Np * 2 * rb, obs_b = TT * E * Np * h->lay.obs_dim * rb;
-  const size_t rew_b = TT * E * Np * rb, done_b = TT * E, info_b = TT * E * 2 * 4;
-  const size_t o_act = 0, o_obs = align_up(o_act + act_b, 256), o_rew = align_up(o_obs + obs_b, 256);
-  const size_t o_done = align_up(o_rew + rew_b, 256), o_info = align_up(o_done + done_b, 256);
-  int rc = ww_stage(h, o_info + info_b);
-  if (rc) return rc;
-  char* st = (char*)h->stage;
-  MADRL_CUDA_CHECK(cudaMemcpyAsync(st + o_act, actions_host, act_b, cudaMemcpyHostToDevice, 0));
-  rc = madrl_ww_rollout(h, T, st + o_act, st + o_obs, st + o_rew, (uint8_t*)(st + o_done),
-                        (int32_t*)(st + o_info), auto_reset, nullptr);
-  if (rc) return rc;
-  MADRL_CUDA_CHECK(cudaMemcpyAsync(obs_host, st + o_obs, obs_b, cudaMemcpyDeviceToHost, 0));
-  MADRL_CUDA_CHECK(cudaMemcpyAsync(rew_host, st + o_rew, rew_b, cudaMemcpyDeviceToHost, 0));
-  MADRL_CUDA_CHECK(cudaMemcpyAsync(done_host, st + o_done, done_b, cudaMemcpyDeviceToHost, 0));
-  MADRL_CUDA_CHECK(cudaMemcpyAsync(info_host, st + o_info, info_b, cudaMemcpyDeviceToHost, 0));
-  MADRL_CUDA_CHECK(cudaStreamSynchronize(0));
-  return MADRL_OK;
+  MADRL_REQUIRE((flags & ~MADRL_HOST_OBS_LAST) == 0, "unknown flags %d", flags);
+  const size_t E = h->cfg.n_envs, Np = h->cfg.n_pursuers, rb = h->lay.real_bytes;
+  const StepBytes sb = {E * Np * 2 * rb, E * Np * h->lay.obs_dim * rb, E * Np * rb, E, E * 2 * 4};
+  return host_rollout(h->pipe, T, sb, actions_host, obs_host, rew_host, done_host, info_host,
+                      flags & MADRL_HOST_OBS_LAST,
+                      [&](int, int Tc, char* a, char* o, char* r, char* d, char* i, cudaStream_t st) {
+                        return madrl_ww_rollout(h, Tc, a, o, r, (uint8_t*)d, (int32_t*)i, auto_reset, st);
+                      });
+}
+
+extern "C" int madrl_ww_rollout_host(madrl_ww* h, int T, const void* actions_host, void* obs_host,
+                                     void* rew_host, uint8_t* done_host, int32_t* info_host,
+                                     int auto_reset) {
+  return madrl_ww_rollout_host2(h, T, actions_host, obs_host, rew_host, done_host, info_host, auto_reset, 0);
 }

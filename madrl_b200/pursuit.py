@@ -55,6 +55,8 @@ class BatchedPursuitEvade(object):
         self._L = _lib.lib()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
             else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         mp = np.ascontiguousarray(np.asarray(map_pool), dtype=np.int32)
         if mp.ndim == 2:
             mp = mp[None]
@@ -124,11 +126,23 @@ class BatchedPursuitEvade(object):
     def reset(self, mask=None, out=None):
         E, Np, D = self.n_envs, self.n_pursuers, self.obs_dim
         obs = out if out is not None else torch.zeros((E, Np, D), dtype=torch.float32, device=self.device)
+        if out is not None:
+            _lib.require_tensor(out, "out", torch.float32, (E, Np, D), self.device)
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         with torch.cuda.device(self.device):
             _lib.check(self._L.madrl_pursuit_reset(self._h, _ptr(mask), _ptr(obs), self._stream()))
         return obs
+
+    def _require_outputs(self, T, out, device):
+        """dtype / shape / contiguity / placement of caller-supplied trajectory buffers."""
+        obs, rew, done, info = out
+        E, A, D = self.n_envs, self.n_pursuers, self.obs_dim
+        _lib.require_tensor(obs, "obs", torch.float32, (T, E, A, D), device)
+        _lib.require_tensor(rew, "rew", torch.float32, (T, E, A), device)
+        _lib.require_tensor(done, "done", torch.uint8, (T, E), device)
+        _lib.require_tensor(info, "info", torch.int32, (T, E) + (), device)
+        return obs, rew, done, info
 
     def rollout(self, actions, auto_reset=True, out=None):
         """actions int32 [T, E, Np] -> (obs [T,E,Np,D] f32, rew [T,E,Np] f32, done [T,E] u8,
@@ -143,7 +157,7 @@ class BatchedPursuitEvade(object):
             done = torch.empty((T, E), dtype=torch.uint8, device=self.device)
             info = torch.empty((T, E), dtype=torch.int32, device=self.device)
         else:
-            obs, rew, done, info = out
+            obs, rew, done, info = self._require_outputs(T, out, self.device)
         with torch.cuda.device(self.device):
             _lib.check(self._L.madrl_pursuit_rollout(self._h, T, _ptr(actions), _ptr(obs), _ptr(rew),
                                                      _ptr(done), _ptr(info), int(auto_reset), self._stream()))
@@ -154,11 +168,20 @@ class BatchedPursuitEvade(object):
         obs, rew, done, info = self.rollout(a, auto_reset=auto_reset)
         return obs[0], rew[0], done[0], dict(removed=info[0])
 
-    def rollout_host(self, actions, obs, rew, done, info, auto_reset=True):
+    def rollout_host(self, actions, obs, rew, done, info, auto_reset=True, obs_last=False):
+        """rollout() with HOST tensors (pinned for full PCIe speed); the copies are inside the call,
+        chunked and overlapped with the compute (csrc/host_pipeline.cuh).  `obs_last=True`: only the last
+        step's observations come back (obs is [E, A, D]) -- the policy-on-device mode."""
         T = actions.shape[0]
+        E, A, D = self.n_envs, self.n_pursuers, self.obs_dim
+        _lib.require_tensor(actions, "actions", torch.int32, (T, E) + (self.n_pursuers,), 'cpu')
+        _lib.require_tensor(obs, "obs", torch.float32, (E, A, D) if obs_last else (T, E, A, D), 'cpu')
+        _lib.require_tensor(rew, "rew", torch.float32, (T, E, A), 'cpu')
+        _lib.require_tensor(done, "done", torch.uint8, (T, E), 'cpu')
+        _lib.require_tensor(info, "info", torch.int32, (T, E) + (), 'cpu')
         with torch.cuda.device(self.device):
-            _lib.check(self._L.madrl_pursuit_rollout_host(self._h, T, _ptr(actions), _ptr(obs), _ptr(rew),
-                                                          _ptr(done), _ptr(info), int(auto_reset)))
+            _lib.check(self._L.madrl_pursuit_rollout_host2(self._h, T, _ptr(actions), _ptr(obs), _ptr(rew), _ptr(done),
+                                                      _ptr(info), int(auto_reset), 1 if obs_last else 0))
         return obs, rew, done, info
 
 

@@ -63,6 +63,8 @@ class BatchedMAWaterWorld(object):
         self._L = _lib.lib()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
             else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.dtype = dtype
         assert dtype in (torch.float32, torch.float64)
         self.n_envs, self.n_pursuers, self.n_evaders, self.n_poison = n_envs, n_pursuers, n_evaders, n_poison
@@ -147,11 +149,23 @@ class BatchedMAWaterWorld(object):
         """reset() of the masked envs (all if None) -> obs [E, Np, D]."""
         E, Np, D = self.n_envs, self.n_pursuers, self.obs_dim
         obs = out if out is not None else torch.zeros((E, Np, D), dtype=self.dtype, device=self.device)
+        if out is not None:
+            _lib.require_tensor(out, "out", self.dtype, (E, Np, D), self.device)
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         with torch.cuda.device(self.device):
             _lib.check(self._L.madrl_ww_reset(self._h, _ptr(mask), _ptr(obs), self._stream()))
         return obs
+
+    def _require_outputs(self, T, out, device):
+        """dtype / shape / contiguity / placement of caller-supplied trajectory buffers."""
+        obs, rew, done, info = out
+        E, A, D = self.n_envs, self.n_pursuers, self.obs_dim
+        _lib.require_tensor(obs, "obs", self.dtype, (T, E, A, D), device)
+        _lib.require_tensor(rew, "rew", self.dtype, (T, E, A), device)
+        _lib.require_tensor(done, "done", torch.uint8, (T, E), device)
+        _lib.require_tensor(info, "info", torch.int32, (T, E) + (2,), device)
+        return obs, rew, done, info
 
     def rollout(self, actions, auto_reset=True, out=None):
         """T lockstep steps in one kernel launch.  actions [T, E, Np, 2] ->
@@ -166,7 +180,7 @@ class BatchedMAWaterWorld(object):
             done = torch.empty((T, E), dtype=torch.uint8, device=self.device)
             info = torch.empty((T, E, 2), dtype=torch.int32, device=self.device)
         else:
-            obs, rew, done, info = out
+            obs, rew, done, info = self._require_outputs(T, out, self.device)
         with torch.cuda.device(self.device):
             _lib.check(self._L.madrl_ww_rollout(self._h, T, _ptr(actions), _ptr(obs), _ptr(rew),
                                                 _ptr(done), _ptr(info), int(auto_reset), self._stream()))
@@ -179,12 +193,20 @@ class BatchedMAWaterWorld(object):
         obs, rew, done, info = self.rollout(a, auto_reset=auto_reset)
         return obs[0], rew[0], done[0], dict(evcatches=info[0, :, 0], pocatches=info[0, :, 1])
 
-    def rollout_host(self, actions, obs, rew, done, info, auto_reset=True):
-        """Same as rollout() but with HOST tensors (pinned or not); copies are inside the call."""
+    def rollout_host(self, actions, obs, rew, done, info, auto_reset=True, obs_last=False):
+        """rollout() with HOST tensors (pinned for full PCIe speed); the copies are inside the call,
+        chunked and overlapped with the compute (csrc/host_pipeline.cuh).  `obs_last=True`: only the last
+        step's observations come back (obs is [E, A, D]) -- the policy-on-device mode."""
         T = actions.shape[0]
+        E, A, D = self.n_envs, self.n_pursuers, self.obs_dim
+        _lib.require_tensor(actions, "actions", self.dtype, (T, E) + (self.n_pursuers, 2), 'cpu')
+        _lib.require_tensor(obs, "obs", self.dtype, (E, A, D) if obs_last else (T, E, A, D), 'cpu')
+        _lib.require_tensor(rew, "rew", self.dtype, (T, E, A), 'cpu')
+        _lib.require_tensor(done, "done", torch.uint8, (T, E), 'cpu')
+        _lib.require_tensor(info, "info", torch.int32, (T, E) + (2,), 'cpu')
         with torch.cuda.device(self.device):
-            _lib.check(self._L.madrl_ww_rollout_host(self._h, T, _ptr(actions), _ptr(obs), _ptr(rew),
-                                                     _ptr(done), _ptr(info), int(auto_reset)))
+            _lib.check(self._L.madrl_ww_rollout_host2(self._h, T, _ptr(actions), _ptr(obs), _ptr(rew), _ptr(done),
+                                                      _ptr(info), int(auto_reset), 1 if obs_last else 0))
         return obs, rew, done, info
 
 

@@ -41,6 +41,10 @@ if __name__ == "__main__":
             run(4096, T, 4, 0, c2, reps=20 if T == 1 else 5)
         for E in (2048, 8192, 16384, 65536):
             run(E, 16, 4, 0, c2)
+    if which == "c2one":
+        run(4096, 256, 4, 0, c2, reps=2)
+    if which == "c4one":
+        run(4096, 16, 4, 0, c4, reps=2)
     if which == "quick":
         run(4096, 256, 4, 0, c2)
         run(4096, 16, 4, 0, c4)

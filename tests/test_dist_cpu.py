@@ -63,6 +63,53 @@ def _worker(rank, world, port, ragged, q):
         dist.destroy_process_group()
 
 
+def _ragged_peer_worker(rank, world, port, q):
+    """the peer-memory exchanges index the root's buffers by rank * local size, so they
+    must refuse ragged shards on EVERY rank (here: the rank-consistency check they call first)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from madrl_b200.dist import _same_on_all_ranks
+        _same_on_all_ranks((5, 3), "shape")                       # equal: passes
+        try:
+            _same_on_all_ranks((2 + rank, 3), "(n_envs, n_agents)")   # 10 envs on 4 ranks -> 2,3,2,3
+            q.put(False)
+        except ValueError as ex:
+            q.put("differs across ranks" in str(ex))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_refuses_ragged_shards():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ragged_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get() is True and q.get() is True
+
+
+def test_packed_trajectory_sections_are_16_byte_aligned():
+    """the kernels store info rows as 8-byte words; with T*E*A odd (fp32) the old layout put
+    the info section at 4 mod 8."""
+    from madrl_b200.dist import PackedTrajectory
+    for T, E, A, w in ((3, 1, 5, 2), (1, 1, 1, 2), (7, 3, 3, 1), (5, 2, 3, 2)):
+        pk = PackedTrajectory(T, E, A, w, "cpu", obs_dim=11, act_shape=(A, 2))
+        for k, (off, n) in pk.offsets.items():
+            assert off % 16 == 0, (k, off)
+            assert getattr(pk, k).data_ptr() - pk.buf.data_ptr() == off
+        assert pk.rew.shape == (T, E, A) and pk.obs.shape == (T, E, A, 11) and pk.act.shape == (T, E, A, 2)
+        assert pk.info.shape == ((T, E, w) if w > 1 else (T, E)) and pk.nbytes % 16 == 0
+        pk.buf.zero_()
+        pk.info.fill_(-1)
+        pk.done.fill_(3)
+        assert float(pk.rew.abs().sum()) == 0 and float(pk.obs.abs().sum()) == 0   # no overlap
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

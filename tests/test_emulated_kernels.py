@@ -688,3 +688,40 @@ def test_host_entry_points_equal_device_entry_points():
         assert np.array_equal(oa, ob.check("obs"))
         for x, y in zip(a.rollout(act, host=False), b.rollout(act, host=True)):
             assert np.array_equal(x, y)
+
+
+def test_pipelined_host_rollout_chunks_and_obs_last_mode():
+    """csrc/host_pipeline.cuh: the host-buffer rollout cut into several chunks (chunk size forced down)
+    must equal the single device launch for every family, and MADRL_HOST_OBS_LAST returns rewards /
+    dones / infos of every step + only the last step's observations."""
+    import ctypes as C
+    from emu.driver import EmuHostage, EmuPursuit, EmuWaterworld, Guarded, _p
+    maps = pool16()
+    mk = [lambda: EmuWaterworld(3, seed=4, max_path_length=7, fp64=False, **WW["c2"]),
+          lambda: EmuPursuit(3, maps, seed=4, max_path_length=7, **C3),
+          lambda: EmuHostage(3, 10, 16, 16, 4, 2, seed=4, max_path_length=7, fp64=False)]
+    T = 13                                   # odd: chunk boundaries must keep the info rows 8-byte aligned
+    acts = [np.random.RandomState(2).randn(T, 3, 5, 2).astype(np.float32),
+            np.random.RandomState(0).randint(0, 5, size=(T, 3, 8)).astype(np.int32),
+            np.random.RandomState(1).randn(T, 3, 10, 2).astype(np.float32)]
+    for make, act in zip(mk, acts):
+        a, b, c = make(), make(), make()
+        for e in (a, b, c):
+            e.reset()
+        ref = a.rollout(act, host=False)
+        b.lib.madrl_set_host_chunk_bytes(ref[0][0].nbytes * 3)          # ~3 steps per chunk -> 5 chunks
+        try:
+            for x, y in zip(ref, b.rollout(act, host=True)):
+                assert np.array_equal(x, y)
+            f = getattr(c.lib, "madrl_%s_rollout_host2" % c.fam)
+            f.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int]
+            E, A = c.n_envs, c.n_agents
+            bufs = [Guarded((E, A, c.obs_dim), c.obs_dtype, np.nan), Guarded((T, E, A), c.obs_dtype, np.nan),
+                    Guarded((T, E), np.uint8, 255), Guarded((T, E) + c.info_shape, np.int32, -1)]
+            assert f(c._h, T, _p(np.ascontiguousarray(act)), *[_p(x.arr) for x in bufs], 1, 1) == 0
+            last, rew, done, info = [x.check("host2") for x in bufs]
+            assert np.array_equal(last, ref[0][-1]) and np.array_equal(rew, ref[1])
+            assert np.array_equal(done, ref[2]) and np.array_equal(info, ref[3])
+            assert f(c._h, T, _p(np.ascontiguousarray(act)), *[_p(x.arr) for x in bufs], 1, 2) == -1   # unknown flag
+        finally:
+            b.lib.madrl_set_host_chunk_bytes(0)

@@ -107,3 +107,30 @@ def test_shard_construction_arguments():
     assert made == dict(n=hi - lo, base=lo, args=(5, 5), kw=dict(seed=1)) and eng.shard == (lo, hi, 4097)
     with pytest.raises(ValueError):
         make_sharded(Fake, 2, rank=0, world=8)      # rank 0 of 8 owns nothing of a 2-env batch
+
+
+def test_require_tensor_rejects_wrong_dtype_shape_layout_and_device():
+    """caller-supplied buffers are validated before their data_ptr() crosses the C ABI."""
+    import pytest
+    import torch
+    from madrl_b200._lib import require_tensor
+    ok = torch.zeros((3, 4, 5), dtype=torch.float32)
+    assert require_tensor(ok, "obs", torch.float32, (3, 4, 5), 'cpu') is ok
+    with pytest.raises(TypeError):
+        require_tensor(ok.double(), "obs", torch.float32, (3, 4, 5), 'cpu')          # fp64 on an fp32 engine
+    with pytest.raises(ValueError):
+        require_tensor(ok[:2], "obs", torch.float32, (3, 4, 5), 'cpu')               # short buffer
+    with pytest.raises(ValueError):
+        require_tensor(ok.transpose(0, 1), "obs", torch.float32, (4, 3, 5), 'cpu')   # non-contiguous view
+    with pytest.raises(ValueError):
+        require_tensor(ok, "obs", torch.float32, (3, 4, 5), torch.device("cuda", 0))  # host tensor for a device slot
+    with pytest.raises(TypeError):
+        require_tensor(ok.numpy(), "obs", torch.float32, (3, 4, 5), 'cpu')
+
+
+def test_stale_library_is_detected_by_content_hash(tmp_path, monkeypatch):
+    """a git-ignored .so built from other sources must not be loaded silently."""
+    from madrl_b200 import build as B
+    assert not B._stale()                     # conftest / an earlier test built it from this tree
+    monkeypatch.setattr(B, "NVCC_FLAGS", B.NVCC_FLAGS + ["-DSOMETHING_ELSE"])
+    assert B._stale()                         # same files, other flags: another binary

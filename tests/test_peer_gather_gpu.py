@@ -46,27 +46,31 @@ def _worker(rank, world, port, q):
                 else:
                     ok = ok and mode == "root" and rank != 0
             pg.close()
-        # copy-engine gather to the root, overlapped on a side stream
+        # copy-engine gather to the root, overlapped on a side stream; both completion protocols
+        # (stream memory operations / round 1's NCCL all-reduce), with the full trajectory packed in
         from madrl_b200.dist import AsyncRootGather
-        ag = AsyncRootGather(T, E, Np, 2, dev)
-        keep = []
-        for k in range(3):
-            act = torch.randn(T, E, Np, 2, device=dev, generator=torch.Generator(dev).manual_seed(7 * k + rank)) * 0.7
-            ag.before_reuse(k)
-            rew_b, done_b, info_b = ag.buffers(k)
-            obs = torch.empty((T, E, Np, eng.obs_dim), device=dev)
-            eng.rollout(act, auto_reset=True, out=(obs, rew_b, done_b, info_b))
-            ag.submit(k)
-            ag.before_reuse(k)                     # wait for this exchange before checking it
-            torch.cuda.synchronize()
-            ref = torch.empty(world * ag.local[0].nbytes, dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(ref, ag.local[k % 2].buf)
-            got = ag.result(k)
-            if rank == 0:
-                ok = ok and torch.equal(got.reshape(-1), ref)
-            else:
-                ok = ok and got is None
-        ag.close()
+        for completion in ("memops", "nccl"):
+            ag = AsyncRootGather(T, E, Np, 2, dev, completion=completion, obs_dim=eng.obs_dim, act_shape=(Np, 2))
+            ok = ok and ag.completion == completion
+            seen = []
+            for k in range(5):                     # > n_sets: exercises the release / reuse handshake
+                act = torch.randn(T, E, Np, 2, device=dev, generator=torch.Generator(dev).manual_seed(7 * k + rank)) * 0.7
+                ag.before_reuse(k)
+                pk = ag.packed(k)
+                pk.act.copy_(act)
+                eng.rollout(pk.act, auto_reset=True, out=(pk.obs, pk.rew, pk.done, pk.info))
+                ag.submit(k, consume=lambda g: seen.append(g.clone()))   # root: snapshot inside the protocol
+                ag.before_reuse(k)                 # wait for this exchange before checking it
+                torch.cuda.synchronize()
+                ref = torch.empty(world * pk.nbytes, dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(ref, pk.buf)
+                got = ag.result(k)
+                if rank == 0:
+                    ok = ok and torch.equal(got.reshape(-1), ref) and torch.equal(seen[-1].reshape(-1), ref)
+                    ok = ok and torch.equal(pk.view_of(got[1], 'obs'), pk.view_of(ref.view(world, -1)[1], 'obs'))
+                else:
+                    ok = ok and got is None and not seen
+            ag.close()
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
