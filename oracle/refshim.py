@@ -196,3 +196,89 @@ def make_reference_pursuit(map_pool, stream, **kwargs):
     au_mod.np = proxy
     env = pe_mod.PursuitEvade(map_pool, evader_controller=StreamController(5, stream), **kwargs)
     return env
+
+
+def load_rllab_callers():
+    """The reference's OWN callers of the env boundary, imported unmodified:
+    ``(RLLabEnv, ma_sampler module, VecEnvExecutor)`` --
+    rllabwrapper/__init__.py:29-90, rllab/rllab/sampler/ma_sampler.py (dec_rollout :52-100),
+    rllab/sandbox/rocky/tf/envs/vec_env_executor.py:6-48.  theano / path.py / the process-pool modules
+    are stubbed (none of them is touched by the code paths used); everything else is the real file."""
+    install()
+    import inspect
+    if not hasattr(inspect, "getargspec"):      # removed in Python 3.11; rllab/core/serializable.py:13 uses it
+        import collections
+        _AS = collections.namedtuple("ArgSpec", "args varargs keywords defaults")
+
+        def getargspec(f):
+            fs = inspect.getfullargspec(f)
+            return _AS(fs.args, fs.varargs, fs.varkw, fs.defaults)
+        inspect.getargspec = getargspec
+    for p in (os.path.join(REFERENCE_ROOT, "rllab"), REFERENCE_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    if "theano" not in sys.modules:
+        th = _module("theano")
+        th.tensor = _module("theano.tensor")
+        th.tensor.nnet = _module("theano.tensor.nnet")
+        th.tensor.extra_ops = _module("theano.tensor.extra_ops")
+        th.config = types.SimpleNamespace(floatX="float32")
+    if "path" not in sys.modules:
+        _module("path", Path=type("Path", (str,), {}))
+    import gym
+    if not hasattr(gym, "envs"):
+        gym.envs = _module("gym.envs")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import rllab.sampler  # noqa: F401  (the real package)
+        for name in ("rllab.sampler.parallel_sampler", "rllab.sampler.stateful_pool"):
+            if name not in sys.modules:
+                _module(name, _get_scoped_G=None, _worker_set_env_params=None, singleton_pool=None)
+        from rllab.sampler import ma_sampler
+        from rllabwrapper import RLLabEnv
+        # sandbox.rocky.tf.misc.tensor_utils is the only import of vec_env_executor.py besides numpy/pickle
+        from rllab.misc import tensor_utils as _tu
+        for name in ("sandbox", "sandbox.rocky", "sandbox.rocky.tf", "sandbox.rocky.tf.misc"):
+            if name not in sys.modules:
+                _module(name)
+        import importlib.util
+        spec = importlib.util.spec_from_file_location(
+            "sandbox.rocky.tf.misc.tensor_utils",
+            os.path.join(REFERENCE_ROOT, "rllab", "sandbox", "rocky", "tf", "misc", "tensor_utils.py"))
+        try:
+            tu = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(tu)
+        except Exception:            # needs tensorflow: the stacking helpers are the same functions in rllab.misc
+            tu = _tu
+        sys.modules["sandbox.rocky.tf.misc.tensor_utils"] = tu
+        sys.modules["sandbox.rocky.tf.misc"].tensor_utils = tu
+        spec = importlib.util.spec_from_file_location(
+            "_ref_vec_env_executor",
+            os.path.join(REFERENCE_ROOT, "rllab", "sandbox", "rocky", "tf", "envs", "vec_env_executor.py"))
+        vee = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(vee)
+    return RLLabEnv, ma_sampler, vee.VecEnvExecutor
+
+
+def load_rltools_samplers():
+    """rltools/rltools/samplers/__init__.py (centrollout / decrollout / concrollout, :98-235) and
+    trajutil.py loaded from their files; ``rltools.nn`` (TensorFlow) is a stub -- only the Sampler base
+    class, which the rollout functions do not use, refers to it."""
+    install()
+    import importlib.util
+    rl = sys.modules["rltools"]
+    if "rltools.nn" not in sys.modules:
+        rl.nn = _module("rltools.nn", Standardizer=object, NoOpStandardizer=object)
+    if "rltools.trajutil" not in sys.modules:
+        spec = importlib.util.spec_from_file_location(
+            "rltools.trajutil", os.path.join(REFERENCE_ROOT, "rltools", "rltools", "trajutil.py"))
+        tj = importlib.util.module_from_spec(spec)
+        sys.modules["rltools.trajutil"] = tj
+        spec.loader.exec_module(tj)
+        rl.trajutil = tj
+    spec = importlib.util.spec_from_file_location(
+        "_ref_rltools_samplers", os.path.join(REFERENCE_ROOT, "rltools", "rltools", "samplers", "__init__.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

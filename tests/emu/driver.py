@@ -233,3 +233,81 @@ class EmuPursuit(_Engine):
                     gone=int(self.view(Ly.gone, np.int64, (E,))[e]),
                     map_id=int(self.view(Ly.map_id, np.int32, (E,))[e]),
                     counter=int(self.view(Ly.rng_counter, np.int64, (E,))[e]))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Test double for the DROP-IN classes (madrl_b200.MAWaterWorld / PursuitEvade / ContinuousHostageWorld):
+# those classes talk to a `Batched*` engine (reset / step / seed / set_params returning torch tensors).
+# `emulated_dropins()` swaps the engine classes for facades over the emulator engines above, so the
+# drop-in code itself -- list-of-arrays returns, float64 conversion, info dicts, spaces, pickling,
+# the vec_env_executor hook -- runs unchanged on a CPU box, against the reference's own callers
+# (tests/test_reference_callers.py).  On a GPU box the same classes run on the real library.
+# ---------------------------------------------------------------------------------------------------
+class _TorchFacade(object):
+    def __init__(self, emu, info_keys):
+        import torch
+        self._t, self.emu, self._keys = torch, emu, info_keys
+        self.n_envs, self.obs_dim = emu.n_envs, emu.obs_dim
+        self.device = torch.device("cpu")
+        self.dtype = torch.float64 if emu.obs_dtype == np.float64 else torch.float32
+
+    def seed(self, seed=None):
+        self.emu.seed(0 if seed is None else int(seed))
+        return [seed]
+
+    def reset(self, mask=None, out=None):
+        return self._t.from_numpy(np.array(self.emu.reset(None if mask is None else np.asarray(mask))))
+
+    def step(self, actions, auto_reset=False):
+        a = np.asarray(actions).reshape((1, self.n_envs) + self._act_tail)
+        obs, rew, done, info = [self._t.from_numpy(np.array(x)) for x in self.emu.rollout(a, auto_reset=auto_reset)]
+        if len(self._keys) == 1:
+            d = {self._keys[0]: info[0]}
+        else:
+            d = {k: info[0, :, i] for i, k in enumerate(self._keys)}
+        return obs[0], rew[0], done[0], d
+
+
+def _ww_facade(n_envs, *args, device=None, dtype=None, **kw):
+    import torch
+    f = _TorchFacade(EmuWaterworld(n_envs, *args, fp64=(dtype == torch.float64), **kw), ("evcatches", "pocatches"))
+    f._act_tail = (f.emu.n_pursuers, 2)
+    return f
+
+
+def _hw_facade(n_envs, *args, device=None, dtype=None, **kw):
+    import torch
+    f = _TorchFacade(EmuHostage(n_envs, *args, fp64=(dtype == torch.float64), **kw), ("ho_saved", "cr_encs"))
+    f._act_tail = (f.emu.n_agents, 2)
+    return f
+
+
+def _pe_facade(n_envs, map_pool, device=None, **kw):
+    f = _TorchFacade(EmuPursuit(n_envs, map_pool, **kw), ("removed",))
+    f._act_tail = (f.emu.n_pursuers,)
+
+    def set_params(catchr, constraint_window):
+        lib = f.emu.lib
+        lib.madrl_pursuit_set_params.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        f.emu._check(lib.madrl_pursuit_set_params(f.emu._h, float(catchr), float(constraint_window)))
+    f.set_params = set_params
+    return f
+
+
+class emulated_dropins(object):
+    """Context manager: madrl_b200's drop-in env classes run on the emulator engines."""
+
+    def __enter__(self):
+        import madrl_b200.hostage as H
+        import madrl_b200.pursuit as P
+        import madrl_b200.waterworld as W
+        self._saved = (W.BatchedMAWaterWorld, P.BatchedPursuitEvade, H.BatchedHostageWorld)
+        W.BatchedMAWaterWorld, P.BatchedPursuitEvade, H.BatchedHostageWorld = _ww_facade, _pe_facade, _hw_facade
+        return self
+
+    def __exit__(self, *exc):
+        import madrl_b200.hostage as H
+        import madrl_b200.pursuit as P
+        import madrl_b200.waterworld as W
+        W.BatchedMAWaterWorld, P.BatchedPursuitEvade, H.BatchedHostageWorld = self._saved
+        return False

@@ -102,7 +102,7 @@ def test_fp64_matches_reference_golden(name):
     assert int(eng.state['rng_counter'][0].item()) == int(g["counter"])
 
 
-@pytest.mark.parametrize("name,E,T,std,min_frac", [("c5", 128, 16, 1.0, 0.95), ("dense", 128, 30, 3.0, 0.9)])
+@pytest.mark.parametrize("name,E,T,std,min_frac", [("c5", 128, 16, 1.0, 0.98), ("dense", 128, 30, 3.0, 0.98)])
 def test_fp32_single_step_teacher_forced(name, E, T, std, min_frac):
     """fp32 production build from its own states vs the float64 oracle, per-predicate exclusion
     (oracle/fragility.py); finished envs are re-initialised so that live envs keep being stepped."""
@@ -128,7 +128,7 @@ def test_fp32_teacher_forced_from_reference_states(name):
     eng.reset()
     log = TF.hw_golden_teacher_forced(TF.TorchAdapter(eng), g, args, kw, "hw_fp32_golden_" + name)
     log.dump(ROOT)
-    assert log.checked_frac >= 0.95 and log.obs_frac >= 0.999, log.d
+    assert log.checked_frac >= 0.98 and log.obs_frac >= 0.999, log.d
 
 
 def test_horizon_without_penalty_and_sharding():

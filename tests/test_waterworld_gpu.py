@@ -99,7 +99,7 @@ def test_fp64_matches_reference_golden(name):
 
 
 @pytest.mark.parametrize("name,E,T,min_frac", [("c2", 256, 24, 0.98), ("dense", 128, 30, 0.98),
-                                               ("c4", 16, 12, 0.9),   # 72 600 predicates per step
+                                               ("c4", 16, 12, 0.98),  # 72 600 predicates per step
                                                ("global_nospeed_randobst", 128, 30, 0.98)])
 def test_fp32_single_step_teacher_forced(name, E, T, min_frac):
     """fp32 production build, one step at a time from its own states, vs the float64 oracle; per-predicate
@@ -126,7 +126,7 @@ def test_fp32_teacher_forced_from_reference_states(name):
     eng.reset()
     log = TF.ww_golden_teacher_forced(TF.TorchAdapter(eng), g, cfg, "ww_fp32_golden_" + name)
     log.dump(ROOT)
-    assert log.checked_frac >= 0.95 and log.obs_frac >= 0.999, log.d
+    assert log.checked_frac >= 0.98 and log.obs_frac >= 0.999, log.d
 
 
 def test_fp32_multi_step_tracks_fp64_build():
