@@ -314,6 +314,23 @@ int madrl_moments_f32(size_t n, const float* a_dev, const float* b_dev, double* 
 int madrl_center_advantages_f32(size_t n, float* adv_dev, int center, int positive, double* stats_dev,
                                 double* workspace_dev, void* stream);
 
+/* Path packing: time-major rollout tensors -> rllab's per-(env, episode, agent) paths
+ * (rllab/rllab/sampler/ma_sampler.py:52-100 `dec_rollout`, episodes cut at `done` as
+ * rllab/sandbox/rocky/tf/envs/vec_env_executor.py:16-28 does).  Paths are ordered (env, episode, agent);
+ * the rows of a path are consecutive in the packed arrays.
+ *   madrl_paths_plan      done uint8 [T][E] -> seg_start / seg_len int32 [T][E] (start and length of the
+ *                         episode containing step t), n_episodes int32 [E], ep_rec int32 [E][T][3] =
+ *                         (start step, length, terminated) of the first n_episodes[e] episodes of env e;
+ *                         path (e, episode j, agent a) occupies rows [e*T*A + s_j*A + a*L_j, +L_j)
+ *   madrl_paths_pack_u32  src [T][E][A][D] of 4-byte words -> dst [E*T*A][D] in path order.  first != NULL:
+ *                         rows are shifted by one step (row t = first[e][a] for t = 0, src[t-1] afterwards):
+ *                         the observation each action was taken in, with first = the observations before
+ *                         the rollout.  Per-env tensors (infos, dones) are packed with A = 1. */
+int madrl_paths_plan(int T, int E, int A, const uint8_t* done_dev, int32_t* seg_start_dev, int32_t* seg_len_dev,
+                     int32_t* n_episodes_dev, int32_t* ep_rec_dev, void* stream);
+int madrl_paths_pack_u32(int T, int E, int A, int D, const void* src_dev, const void* first_dev,
+                         const int32_t* seg_start_dev, const int32_t* seg_len_dev, void* dst_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

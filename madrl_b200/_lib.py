@@ -121,6 +121,8 @@ def _declare(lib):
     lib.madrl_standardize_f32.argtypes = [i32, C.c_size_t, vp, vp, vp, C.c_double, C.c_double, i32,
                                           C.c_double, i32, vp]
     lib.madrl_episode_stats_f32.argtypes = [i32, i32, i32, vp, vp, C.c_double, i32, vp, vp, vp, vp, vp, vp]
+    lib.madrl_paths_plan.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.madrl_paths_pack_u32.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.madrl_moments_f32.argtypes = [C.c_size_t, vp, vp, vp, vp, vp]
     lib.madrl_center_advantages_f32.argtypes = [C.c_size_t, vp, i32, i32, vp, vp, vp]
     lib.madrl_hostage_state_layout.argtypes = [C.POINTER(HWConfig), C.POINTER(HWLayout)]

@@ -244,6 +244,58 @@ __global__ void center_apply_kernel(size_t n, float* __restrict__ x, const doubl
   }
 }
 
+
+// ---- path packing: time-major rollout tensors -> rllab's per-(env, episode, agent) paths --------
+// (rllab/rllab/sampler/ma_sampler.py:52-100 dec_rollout returns one path dict per agent with
+// `observations / actions / rewards / env_infos` arrays; VecEnvExecutor cuts episodes at `done`,
+// rllab/sandbox/rocky/tf/envs/vec_env_executor.py:16-28.)  Every (t, env, agent) row of a rollout
+// belongs to exactly one path, so packing is a permutation of rows: paths are ordered (env, episode,
+// agent) like the host `to_paths`, the rows of a path are consecutive, and row (t, e, a) lands at
+//     e*T*A + s*A + a*L + (t - s)        s, L = start and length of the episode containing t.
+// paths_plan_kernel: one thread per env walks `done` once (T bytes) and writes s / L per (t, env),
+// the per-episode records and the episode count; paths_pack_kernel: one warp per source row, coalesced
+// reads and writes of D 4-byte words -- a pure HBM-bound permutation (2 x the tensor's bytes).
+__global__ void paths_plan_kernel(int T, int E, int A, const uint8_t* __restrict__ done,
+                                  int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_len,
+                                  int32_t* __restrict__ n_episodes, int32_t* __restrict__ ep_rec) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int s = 0, n = 0;
+  for (int t = 0; t < T; ++t) {
+    const bool end = done[(size_t)t * E + e] != 0;
+    if (end || t == T - 1) {
+      const int L = t + 1 - s;
+      for (int u = s; u <= t; ++u) { seg_start[(size_t)u * E + e] = s; seg_len[(size_t)u * E + e] = L; }
+      // episode record n of this env (at most T episodes): start step, length, terminated
+      int32_t* r = ep_rec + 3 * ((size_t)e * T + n);
+      r[0] = s; r[1] = L; r[2] = end ? 1 : 0;
+      ++n;
+      s = t + 1;
+    }
+  }
+  n_episodes[e] = n;
+}
+
+__global__ void paths_pack_kernel(int T, int E, int A, int D, const uint32_t* __restrict__ src,
+                                  const uint32_t* __restrict__ first, const int32_t* __restrict__ seg_start,
+                                  const int32_t* __restrict__ seg_len, uint32_t* __restrict__ dst) {
+  const size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // source row (t, e, a)
+  const int lane = threadIdx.x & 31;
+  const size_t rows = (size_t)T * E * A;
+  if (row >= rows) return;
+  const int a = (int)(row % A);
+  const size_t te = row / A;
+  const int e = (int)(te % E), t = (int)(te / E);
+  const int s = seg_start[te], L = seg_len[te];
+  // `first` != NULL: observations are shifted by one step -- the row of time t is the observation the
+  // action of time t was taken in: first[e][a] for t = 0, src[t-1] afterwards (on a done step the
+  // rollout's obs slot already holds the reset observation, i.e. the next episode's first one)
+  const uint32_t* in = first ? (t == 0 ? first + ((size_t)e * A + a) * D : src + (row - (size_t)E * A) * D)
+                             : src + row * D;
+  uint32_t* out = dst + ((size_t)e * T * A + (size_t)s * A + (size_t)a * L + (t - s)) * D;
+  for (int d = lane; d < D; d += 32) __stcs(out + d, __ldcs(in + d));
+}
+
 }  // namespace madrl
 
 using namespace madrl;
@@ -335,4 +387,31 @@ extern "C" int madrl_moments_f32(size_t n, const float* a_dev, const float* b_de
   MADRL_REQUIRE(n >= 1, "bad sizes");
   MADRL_REQUIRE(a_dev && stats_dev && workspace_dev, "NULL buffer");
   return run_moments(n, a_dev, b_dev, stats_dev, workspace_dev, (cudaStream_t)stream);
+}
+
+extern "C" int madrl_paths_plan(int T, int E, int A, const uint8_t* done_dev, int32_t* seg_start_dev,
+                                int32_t* seg_len_dev, int32_t* n_episodes_dev, int32_t* ep_rec_dev, void* stream) {
+  MADRL_REQUIRE(T >= 1 && E >= 1 && A >= 1, "bad shape");
+  MADRL_REQUIRE((size_t)T * E * A < ((size_t)1 << 31), "T*E*A must be < 2^31 (row offsets are int32)");
+  MADRL_REQUIRE(done_dev && seg_start_dev && seg_len_dev && n_episodes_dev && ep_rec_dev, "NULL pointer");
+  MADRL_LAUNCH(paths_plan_kernel, (E + 127) / 128, 128, 0, (cudaStream_t)stream, T, E, A, done_dev, seg_start_dev,
+               seg_len_dev, n_episodes_dev, ep_rec_dev);
+  g_launches.fetch_add(1);
+  MADRL_CUDA_CHECK(cudaGetLastError());
+  return MADRL_OK;
+}
+
+extern "C" int madrl_paths_pack_u32(int T, int E, int A, int D, const void* src_dev, const void* first_dev,
+                                    const int32_t* seg_start_dev, const int32_t* seg_len_dev, void* dst_dev,
+                                    void* stream) {
+  MADRL_REQUIRE(T >= 1 && E >= 1 && A >= 1 && D >= 1, "bad shape");
+  MADRL_REQUIRE(src_dev && seg_start_dev && seg_len_dev && dst_dev, "NULL pointer");
+  const size_t rows = (size_t)T * E * A;
+  const size_t blocks = (rows * 32 + 255) / 256;
+  MADRL_REQUIRE(blocks < ((size_t)1 << 31), "too many rows for one launch");
+  MADRL_LAUNCH(paths_pack_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, T, E, A, D, (const uint32_t*)src_dev,
+               (const uint32_t*)first_dev, seg_start_dev, seg_len_dev, (uint32_t*)dst_dev);
+  g_launches.fetch_add(1);
+  MADRL_CUDA_CHECK(cudaGetLastError());
+  return MADRL_OK;
 }

@@ -201,3 +201,90 @@ def to_paths(obs, actions, rew, done, infos=None):
                                   env=e, agent=a, terminated=bool(done[end - 1, e])))
             start = end
     return paths
+
+
+class PackedPaths(object):
+    """rllab-style paths of one rollout, resident on the device (see `pack_paths`).
+
+    ``observations [N, D]``, ``actions [N, ...]``, ``rewards [N]`` with N = T*E*A rows in path order;
+    ``env_infos[k] [E*T]`` in (env, time) order; per path p (ordered env, episode, agent -- the order of
+    the host ``to_paths``): ``offset[p]``, ``length[p]``, ``env[p]``, ``agent[p]``, ``terminated[p]`` and
+    ``info_offset[p]`` (first row of the path's steps in the env_infos arrays).
+    """
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def __len__(self):
+        return int(self.offset.shape[0])
+
+    def path(self, p):
+        """Path p as the dict ``dec_rollout`` returns (ma_sampler.py:88-100); zero-copy views."""
+        o, n, io = int(self.offset[p]), int(self.length[p]), int(self.info_offset[p])
+        return dict(observations=self.observations[o:o + n], actions=self.actions[o:o + n],
+                    rewards=self.rewards[o:o + n],
+                    env_infos={k: v[io:io + n] for k, v in self.env_infos.items()},
+                    env=int(self.env[p]), agent=int(self.agent[p]), terminated=bool(self.terminated[p]))
+
+    def to_list(self):
+        """All paths as NumPy dicts (ONE device->host copy per packed array, then views)."""
+        host = PackedPaths(**{k: (v.cpu().numpy() if torch.is_tensor(v) else
+                                  ({kk: vv.cpu().numpy() for kk, vv in v.items()} if isinstance(v, dict) else v))
+                              for k, v in self.__dict__.items()})
+        return [host.path(p) for p in range(len(host))]
+
+
+def pack_paths(obs, actions, rew, done, infos=None, obs_before=None):
+    """Device-side ``to_paths``: rollout tensors [T,E,A,...] (CUDA) -> `PackedPaths`.
+
+    Episodes are cut at ``done`` (and at the end of the rollout).  ``obs_before`` [E,A,D] = the
+    observations the first actions were taken in (the reset / previous rollout's last observations):
+    when given, ``obs`` is what ``engine.rollout(auto_reset=True)`` returned (the observation AFTER each
+    step, the reset observation on a done step) and the packed ``observations`` are shifted so that row t
+    is the observation action t was taken in -- what rllab stores (ma_sampler.py:71-77).  Without it,
+    ``obs`` is used as is (the host ``to_paths`` contract).  Two kernels of csrc/postproc.cu: a plan pass
+    over ``done`` and one HBM-bound row permutation per tensor; no host loop."""
+    L = _lib.lib()
+    T, E, A = rew.shape
+    dev = rew.device
+    done = done.contiguous()
+    seg_s = torch.empty((T, E), dtype=torch.int32, device=dev)
+    seg_l = torch.empty((T, E), dtype=torch.int32, device=dev)
+    n_ep = torch.empty((E,), dtype=torch.int32, device=dev)
+    ep_rec = torch.zeros((E, T, 3), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        _lib.check(L.madrl_paths_plan(T, E, A, _ptr(done), _ptr(seg_s), _ptr(seg_l), _ptr(n_ep), _ptr(ep_rec), st))
+
+        def pack(x, per_agent, first=None):
+            x = x.contiguous()
+            assert x.element_size() == 4 and x.shape[0] == T and x.shape[1] == E, (x.dtype, x.shape)
+            assert not per_agent or x.shape[2] == A, x.shape
+            n_agents = A if per_agent else 1
+            tail = tuple(x.shape[3:] if per_agent else x.shape[2:])
+            D = max(1, int(np.prod(tail)))
+            out = torch.empty((T * E * n_agents,) + tail, dtype=x.dtype, device=dev)
+            if first is not None:
+                first = first.to(x.dtype).contiguous()
+                assert first.shape == x.shape[1:], (first.shape, x.shape)
+            # per-env tensors (n_agents = 1): the row offset e*T + s + (t - s) = e*T + t for any (s, L)
+            _lib.check(L.madrl_paths_pack_u32(T, E, n_agents, D, _ptr(x), _ptr(first), _ptr(seg_s), _ptr(seg_l),
+                                              _ptr(out), st))
+            return out
+
+        packed_obs = pack(obs, True, obs_before)
+        packed_act = pack(actions, True)
+        packed_rew = pack(rew, True)
+        packed_info = {k: pack(v, False) for k, v in (infos or {}).items()}
+    # per-path records from the (tiny) per-episode records: plain tensor ops, no host loop
+    slot = torch.arange(T, device=dev).unsqueeze(0)
+    live = slot < n_ep.unsqueeze(1)                                   # [E, T] valid episode slots
+    e_idx, _ = torch.nonzero(live, as_tuple=True)
+    rec = ep_rec[live]                                                # [n_episodes_total, 3] in (env, episode) order
+    s, Ln, term = rec[:, 0].long(), rec[:, 1].long(), rec[:, 2]
+    a_idx = torch.arange(A, device=dev)
+    offset = ((e_idx * T * A + s * A).unsqueeze(1) + a_idx.unsqueeze(0) * Ln.unsqueeze(1)).reshape(-1)
+    rep = lambda v: v.unsqueeze(1).expand(-1, A).reshape(-1)          # noqa: E731
+    return PackedPaths(observations=packed_obs, actions=packed_act, rewards=packed_rew, env_infos=packed_info,
+                       offset=offset, length=rep(Ln), env=rep(e_idx), agent=a_idx.repeat(rec.shape[0]),
+                       terminated=rep(term).bool(), info_offset=rep(e_idx * T + s))

@@ -133,3 +133,52 @@ def test_moments_and_advantage_centring(lib):
             if positive:
                 w = po.shift_advantages_to_positive(w)
             assert np.abs(x - w).max() <= 1e-5 * max(1.0, np.abs(w).max())
+
+
+def test_path_packing_kernels_equal_host_to_paths(lib):
+    """madrl_paths_plan + madrl_paths_pack_u32 (the device-side `to_paths`) against the host triple
+    loop of madrl_b200.postproc.to_paths: same paths in the same order, with and without the one-step
+    observation shift."""
+    from madrl_b200.postproc import to_paths
+    vp, i32 = C.c_void_p, C.c_int
+    lib.madrl_paths_plan.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.madrl_paths_pack_u32.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    rs = np.random.RandomState(4)
+    for T, E, A, D, p_done in ((30, 5, 3, 7, 0.12), (9, 2, 1, 40, 0.4), (17, 3, 4, 1, 0.0)):
+        obs = rs.randn(T, E, A, D).astype(np.float32)
+        obs_before = rs.randn(E, A, D).astype(np.float32)
+        act = rs.randint(0, 5, size=(T, E, A)).astype(np.int32)
+        rew = rs.randn(T, E, A).astype(np.float32)
+        info = rs.randint(0, 9, size=(T, E)).astype(np.int32)
+        done = (rs.rand(T, E) < p_done).astype(np.uint8)
+        seg_s, seg_l = np.full((T, E), -1, np.int32), np.full((T, E), -1, np.int32)
+        n_ep, ep_rec = np.zeros(E, np.int32), np.zeros((E, T, 3), np.int32)
+        assert lib.madrl_paths_plan(T, E, A, _p(done), _p(seg_s), _p(seg_l), _p(n_ep), _p(ep_rec), None) == 0
+
+        def pack(x, n_agents, first=None, per_agent=True):
+            tail = x.shape[3:] if per_agent else x.shape[2:]
+            out = np.zeros((T * E * n_agents,) + tail, x.dtype)
+            Dw = max(1, int(np.prod(tail)))
+            assert lib.madrl_paths_pack_u32(T, E, n_agents, Dw, _p(np.ascontiguousarray(x)), _p(first), _p(seg_s),
+                                            _p(seg_l), _p(out), None) == 0
+            return out
+        for shifted in (False, True):
+            p_obs = pack(obs, A, obs_before if shifted else None)
+            p_act, p_rew, p_info = pack(act, A), pack(rew, A), pack(info, 1, per_agent=False)
+            src_obs = np.concatenate([obs_before[None], obs[:-1]]) if shifted else obs
+            want = to_paths(src_obs, act, rew, done, dict(k=info))
+            got = []
+            for e in range(E):
+                for j in range(n_ep[e]):
+                    s, L, term = ep_rec[e, j]
+                    for a in range(A):
+                        o = e * T * A + s * A + a * L
+                        got.append(dict(observations=p_obs[o:o + L], actions=p_act[o:o + L], rewards=p_rew[o:o + L],
+                                        env_infos=dict(k=p_info[e * T + s:e * T + s + L]), env=e, agent=a,
+                                        terminated=bool(term)))
+            assert len(got) == len(want)
+            for g, w in zip(got, want):
+                assert (g['env'], g['agent'], g['terminated']) == (w['env'], w['agent'], w['terminated'])
+                for k in ('observations', 'actions', 'rewards'):
+                    assert np.array_equal(g[k], w[k]), k
+                assert np.array_equal(g['env_infos']['k'], w['env_infos']['k'])

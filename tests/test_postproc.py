@@ -241,3 +241,36 @@ def test_cuda_batch_statistics_match_oracle():
     assert explained_variance(torch.as_tensor(rs.randn(64).astype(np.float32), device='cuda'), const) == 0
     out = center_advantages(const.clone(), inplace=True)                  # zero variance: 0 / 1e-8
     assert torch.equal(out, torch.zeros_like(out))
+
+
+@pytest.mark.gpu
+def test_cuda_pack_paths_matches_host_to_paths():
+    """Device-side path packing (csrc/postproc.cu paths_plan / paths_pack kernels, SURVEY 8f row 1:
+    dec_rollout-shaped paths, rllab/rllab/sampler/ma_sampler.py:52-100) on a real Waterworld rollout
+    with auto-reset, against the host `to_paths` triple loop."""
+    import torch
+    from madrl_b200 import BatchedMAWaterWorld
+    from madrl_b200.postproc import pack_paths, to_paths
+    E, T, mpl = 37, 50, 11
+    eng = BatchedMAWaterWorld(E, 5, 5, n_coop=1, radius=0.04, seed=3, max_path_length=mpl)
+    obs0 = eng.reset().clone()
+    act = torch.randn(T, E, 5, 2, device="cuda") * 0.7
+    obs, rew, done, info = eng.rollout(act, auto_reset=True)
+    infos = dict(evcatches=info[..., 0].contiguous(), pocatches=info[..., 1].contiguous())
+    pp = pack_paths(obs, act, rew, done, infos, obs_before=obs0)
+    shifted = torch.cat([obs0.unsqueeze(0), obs[:-1]]).cpu()
+    want = to_paths(shifted, act.cpu(), rew.cpu(), done.cpu(), {k: v.cpu() for k, v in infos.items()})
+    got = pp.to_list()
+    assert len(got) == len(want) == len(pp) and len(got) > E * 5 * (T // mpl)
+    for g, w in zip(got, want):
+        assert (g['env'], g['agent'], g['terminated']) == (w['env'], w['agent'], w['terminated'])
+        for k in ('observations', 'actions', 'rewards'):
+            assert np.array_equal(g[k], w[k]), k
+        for k in infos:
+            assert np.array_equal(g['env_infos'][k], w['env_infos'][k])
+    one = pp.path(7)                       # zero-copy device views of one path
+    assert one['observations'].is_cuda and one['observations'].shape == (int(pp.length[7]), eng.obs_dim)
+    # a rollout without any done: one path per (env, agent) covering the whole rollout
+    pp2 = pack_paths(obs, act, rew, torch.zeros_like(done), None)
+    assert len(pp2) == E * 5 and int(pp2.length.min()) == T
+    assert torch.equal(pp2.path(6)['observations'], obs[:, 1, 1])
