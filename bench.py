@@ -127,11 +127,11 @@ def measured_traffic():
     for the binary it was captured on: the file records the source hash of that build."""
     p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
-        from madrl_b200.build import source_hash
-        d = json.load(open(p))
-        return d["kernels"], d.get("build_hash") == source_hash(), d.get("build_hash", "")[:12]
+        from madrl_b200.build import kernel_hash
+        d = json.load(open(p))["kernels"]
+        return {k: v for k, v in d.items() if v.get("kernel_hash") == kernel_hash(k.split("_")[0])}
     except Exception:
-        return {}, False, ""
+        return {}
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -386,9 +386,8 @@ def roofline_of(wl, E, T, kern_ms):
     bpe = bytes_per_env_step(wl)
     peak, peak_kind = measured_peak_gbs()
     achieved = bpe * E * T / (kern_ms * 1e-3) / 1e9
-    traffic, fresh, thash = measured_traffic()
     key = WORKLOADS[wl]["key"]
-    dram = traffic.get(key, {}).get("dram_bytes_per_env_step") if fresh else None
+    dram = measured_traffic().get(key, {}).get("dram_bytes_per_env_step")
     out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
            "peak_kind": peak_kind, "kernel": WORKLOADS[wl]["kernel"], "kernel_ms": kern_ms,
            "algorithmic_bytes_per_env_step": bpe,
@@ -399,8 +398,8 @@ def roofline_of(wl, E, T, kern_ms):
            "traffic_unit": "bytes per launch (algorithmic: %d)" % (bpe * E * T),
            "frac_dram": (dram * E * T / (kern_ms * 1e-3) / 1e9 / peak) if dram else None,
            "dram_bytes_per_env_step": dram}
-    if not fresh:
-        out["traffic_note"] = "profiles/r2_traffic.json was captured on another build (%s)" % thash
+    if dram is None:
+        out["traffic_note"] = "no ncu capture of this kernel's current source in profiles/r2_traffic.json"
     return out
 
 

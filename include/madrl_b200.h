@@ -170,7 +170,8 @@ typedef struct madrl_pursuit_config {
   int32_t n_catch, surround;          /* pursuit_evade.py:79,142                                 */
   int32_t reward_global, include_id, sample_maps;
   int32_t max_path_length;            /* VecEnvExecutor horizon, 0 = none                        */
-  int32_t _pad;
+  int32_t max_opponents;              /* random_opponents (pursuit_evade.py:81-82,177-181): > 0 = every reset
+                                         draws randint(1, max_opponents) live evaders (<= n_evaders); 0 = off */
   double layer_norm, catchr, term_pursuit, urgency_reward, constraint_window;
   uint64_t seed;
 } madrl_pursuit_config;

@@ -46,7 +46,7 @@ class PEConfig(C.Structure):
         ("n_evaders", C.c_int32), ("xs", C.c_int32), ("ys", C.c_int32), ("n_maps", C.c_int32),
         ("obs_range", C.c_int32), ("flatten", C.c_int32), ("n_catch", C.c_int32),
         ("surround", C.c_int32), ("reward_global", C.c_int32), ("include_id", C.c_int32),
-        ("sample_maps", C.c_int32), ("max_path_length", C.c_int32), ("_pad", C.c_int32),
+        ("sample_maps", C.c_int32), ("max_path_length", C.c_int32), ("max_opponents", C.c_int32),
         ("layer_norm", C.c_double), ("catchr", C.c_double), ("term_pursuit", C.c_double),
         ("urgency_reward", C.c_double), ("constraint_window", C.c_double), ("seed", C.c_uint64),
     ]

@@ -35,6 +35,19 @@ def source_hash():
     return h.hexdigest()
 
 
+def kernel_hash(family):
+    """sha256 over the files one env kernel is compiled from (its .cu + the shared headers) + the nvcc
+    flags: what a committed ncu capture of that kernel is valid for (profiles/r2_traffic.json)."""
+    import hashlib
+    src = {"ww": "waterworld.cu", "pe": "pursuit.cu", "hw": "hostage.cu"}[family]
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for name in (src, "common.cuh", "philox.cuh", "host_pipeline.cuh"):
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(name.encode())
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale():
     """True if the library is missing or was built from other sources than the ones in the tree."""
     if not os.path.exists(LIB) or not os.path.exists(LIB + ".srchash"):

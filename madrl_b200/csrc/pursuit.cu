@@ -30,7 +30,7 @@ namespace madrl {
 
 struct PEParams {
   int E, env_id_base, Np, Ne, R, off, xs, ys, n_maps, D;
-  int n_catch, surround, reward_global, include_id, sample_maps, max_path_length, flatten;
+  int n_catch, surround, reward_global, include_id, sample_maps, max_path_length, flatten, max_opponents;
   int T, mode, auto_reset;
   size_t obs_step, agent_step;    // element strides of one lockstep step: E*Np*D and E*Np
   int smem_per_warp, cells_pad;   // bytes of shared memory per warp; xs*ys rounded up to 32
@@ -155,6 +155,9 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
           // ---- reset(): pe:173-203.  All lanes run the same stream (warp-uniform). ------------
           SeqStream rs;
           rs.init(p.seed, env_id, 0u, ctr);
+          // pe:177-181 random_opponents: this episode has randint(1, max_opponents) evaders; the others
+          // never exist (not spawned, no draws, not live)
+          const int n_ev = p.max_opponents > 0 ? rs.next_range(1, p.max_opponents) : Ne;
           if (p.sample_maps) map_id = rs.next_range(0, p.n_maps);                    // pe:183
           map = p.maps + (size_t)map_id * ncell;
           const double span = 1.0 - p.constraint_window;
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
           const double yws = 0.0 + (span - 0.0) * rs.next_unit<double>();             // pe:186
           const int xl = (int)((double)xs * xws), xu = (int)((double)xs * (xws + p.constraint_window));
           const int yl = (int)((double)ys * yws), yu = (int)((double)ys * (yws + p.constraint_window));
-          for (int a = 0; a < Nag; ++a) {                                             // au:31-47
+          for (int a = 0; a < Np + n_ev; ++a) {                                       // au:31-47
             int x, y;
             do {
               x = rs.next_range(xl, xu);
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
           ctr = rs.counter;
           ts = 0;
 #pragma unroll
-          for (int c = 0; c < EPL; ++c) live[c] = __ballot_sync(FULL_MASK, lane + 32 * c < Ne);
+          for (int c = 0; c < EPL; ++c) live[c] = __ballot_sync(FULL_MASK, lane + 32 * c < n_ev);
           rebuild = true;
         }
         if (rebuild) {   // cell words from scratch: building flag + occupancy counts
@@ -438,6 +441,10 @@ static int pe_validate(const madrl_pursuit_config* c) {
   MADRL_REQUIRE(c->obs_range >= 1 && c->obs_range * c->obs_range <= 128, "obs_range must be in [1,11]");
   MADRL_REQUIRE(c->layer_norm != 0.0, "layer_norm must be non-zero");
   MADRL_REQUIRE(c->constraint_window > 0.0 && c->constraint_window <= 1.0, "constraint_window must be in (0,1]");
+  // random_opponents: randint(1, max_opponents) evaders per episode; the reference indexes its
+  // evaders_gone array (sized n_evaders at construction) with them (pursuit_evade.py:138,477-487)
+  MADRL_REQUIRE(c->max_opponents == 0 || (c->max_opponents >= 2 && c->max_opponents - 1 <= c->n_evaders),
+                "max_opponents must be 0 (off) or in [2, n_evaders + 1], got %d", c->max_opponents);
   return MADRL_OK;
 }
 
@@ -565,6 +572,7 @@ static int pe_launch(madrl_pursuit* h, int mode, int T, const int32_t* actions, 
   p.xs = c.xs; p.ys = c.ys; p.n_maps = c.n_maps; p.D = h->lay.obs_dim;
   p.n_catch = c.n_catch; p.surround = c.surround; p.reward_global = c.reward_global;
   p.include_id = c.include_id; p.sample_maps = c.sample_maps; p.max_path_length = c.max_path_length;
+  p.max_opponents = c.max_opponents;
   p.flatten = c.flatten;
   p.T = T; p.mode = mode; p.auto_reset = auto_reset;
   p.obs_step = (size_t)p.E * p.Np * p.D; p.agent_step = (size_t)p.E * p.Np;

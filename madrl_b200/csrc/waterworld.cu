@@ -128,18 +128,18 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
   const int warp_stride = gridDim.x;
   const int eLo = p.Np, eHi = p.Np + p.Ne, Nall = p.Nall;
   constexpr bool SMEM = OPL >= 2;
+  constexpr bool ACT_PIPE = OPL <= 2;   // next step's action double-buffered in registers
   extern __shared__ __align__(16) unsigned char ww_smem[];
   // this warp's candidate slots (32-bit shared address)
   const uint32_t slots = SMEM ? smem_addr(ww_smem) : 0u;
 
   // ---- per-lane constants: this lane as OBJECT (classes, thresholds) and as SENSOR -----------
-  real cull2_l[OPL], coll2_l[OPL];
+  real coll2_l[OPL];
   unsigned mE[OPL], mP[OPL], mU[OPL];  // warp-uniform class masks of each object chunk
 #pragma unroll
   for (int c = 0; c < OPL; ++c) {
     const int o = lane + 32 * c;
     const bool isU = o < eLo, isE = o >= eLo && o < eHi, isP = o >= eHi && o < Nall;
-    cull2_l[c] = (o < Nall) ? p.cull2 : (real)-1;
     coll2_l[c] = isE ? p.coll2_e : (isP ? p.coll2_po : (real)-1);
     mU[c] = __ballot_sync(FULL_MASK, isU);
     mE[c] = __ballot_sync(FULL_MASK, isE);
@@ -166,8 +166,10 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     for (int c = 0; c < OPL; ++c) {
       const int o = lane + 32 * c;
       const bool v = o < Nall;
-      x[c] = v ? rec[o] : (real)0;
-      y[c] = v ? rec[Nall + o] : (real)0;
+      // lanes beyond the last object sit far outside every range test (never written back), so the
+      // cull / collision thresholds need no per-lane validity term
+      x[c] = v ? rec[o] : (real)1e15;
+      y[c] = v ? rec[Nall + o] : (real)1e15;
       vx[c] = v ? rec[2 * Nall + o] : (real)0;
       vy[c] = v ? rec[3 * Nall + o] : (real)0;
       col[c] = 0u;
@@ -182,6 +184,9 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     size_t te = (size_t)e;   // index of (t, e) in the [T][E] done / info tensors
     int pass = (p.mode == 1) ? 1 : 0;  // pass 1 = reset pass: fresh draws, zero action, obs only
     const V2* act_t = reinterpret_cast<const V2*>(p.actions) + (size_t)e * p.Np + lane;
+    V2 act_nx;
+    act_nx.x = 0; act_nx.y = 0;
+    if (ACT_PIPE && p.mode == 0 && lane < p.Np) act_nx = *act_t;
 
     // staging registers of the fused exchange
     const int rew_per = 32 / p.Np;                       // steps per coalesced reward run
@@ -193,11 +198,14 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     int sc_rew = 0;
 
     for (int t = 0; t < p.T; ++t) {
-      V2 act;
-      act.x = 0; act.y = 0;
-      if (p.mode == 0 && lane < p.Np) {
+      // this step's action was loaded one step ago; the load of the next one is issued now and is
+      // consumed ~800 instructions later (the FMUL behind a just-in-time load was the kernel's top stall)
+      V2 act = act_nx;
+      if (ACT_PIPE) {
+        if (p.mode == 0 && lane < p.Np && t + 1 < p.T) act_nx = act_t[p.agent_step];
+      } else if (p.mode == 0 && lane < p.Np) {   // big configurations: no registers to spare, latency is hidden anyway
         act = *act_t;
-        if (t + 1 < p.T) prefetch_l1(act_t + p.agent_step);   // next step's action -> L1
+        if (t + 1 < p.T) prefetch_l1(act_t + p.agent_step);
       }
       bool need_reset;
       do {
@@ -273,26 +281,26 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
           }
           if constexpr (SMEM) {
             constexpr uint32_t S = CandSlot<real>::kStride;
-            uint32_t endU = slots, nEc = 0u, nPc = 0u, top = slots;
+            // slot = rank among the candidates in ascending object index; classes are contiguous in
+            // object index, so the class boundaries in slot order are cumulative counts
+            uint32_t nU = 0u, nUE = 0u, top = 0u;
 #pragma unroll
             for (int c = 0; c < OPL; ++c) {
               // lanes as OBJECTS: geometry, collisions (ww:278-293), conservative range cull, staging
               const real rx = x[c] - mx, ry = y[c] - my;
               const real d2 = rx * rx + ry * ry;
-              const bool near = d2 <= cull2_l[c] && !(c == 0 && lane == pi);   // ww:70-71 `same`
+              const bool near = d2 <= p.cull2 && !(c == 0 && lane == pi);   // ww:70-71 `same`
               const unsigned cm = __ballot_sync(FULL_MASK, near);
               const bool hit = d2 <= coll2_l[c];
               if (hit) col[c] |= 1u << pi;
-              // slot = rank among the candidates in ascending object index (= lane + 32 c)
-              if (near) CandSlot<real>::put(top + (uint32_t)__popc(cm & ((1u << lane) - 1u)) * S, rx, ry, d2, vx[c], vy[c]);
-              if (c == 0) endU = slots + (uint32_t)__popc(cm & mU[0]) * S;   // pursuers live in chunk 0 (Np <= 32)
-              nEc += (uint32_t)__popc(cm & mE[c]);
-              nPc += (uint32_t)__popc(cm & mP[c]);
-              top += (uint32_t)__popc(cm) * S;
+              if (near) CandSlot<real>::put(slots + (top + (uint32_t)__popc(cm & lanemask_lt())) * S, rx, ry, d2, vx[c], vy[c]);
+              if (c == 0) nU = (uint32_t)__popc(cm & mU[0]);   // pursuers live in chunk 0 (Np <= 32)
+              nUE += (uint32_t)__popc(cm & (mU[c] | mE[c]));
+              top += (uint32_t)__popc(cm);
             }
             __syncwarp();
-            // lanes as SENSORS: classes are contiguous in object index, hence in slot order U, E, P
-            const uint32_t endE = endU + nEc * S, endP = endE + nPc * S;
+            // lanes as SENSORS: slot order is U, E, P
+            const uint32_t endU = slots + nU * S, endE = slots + nUE * S, endP = slots + top * S;
             const real up = p.range_up;   // `sv < up` <=> `sv <= range`; a best below `up` <=> sensed
             uint32_t aE[KCH], aP[KCH], aU[KCH];
 #pragma unroll
@@ -349,7 +357,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
             // lanes as OBJECTS: geometry, collisions (ww:278-293), conservative range cull
             const real rx = x[c] - mx, ry = y[c] - my;
             const real d2 = rx * rx + ry * ry;
-            unsigned cm = __ballot_sync(FULL_MASK, d2 <= cull2_l[c]);
+            unsigned cm = __ballot_sync(FULL_MASK, d2 <= p.cull2);
             if (c == 0) cm &= ~(1u << pi);  // ww:70-71 `same`
             const bool hit = d2 <= coll2_l[c];
             if (hit) col[c] |= 1u << pi;
@@ -419,6 +427,15 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
         // ---- catches, respawn, rewards: ww:285,293,358-385 -----------------------------------------
         unsigned whoE = 0u, whoP = 0u, whoEnc = 0u;
         int nE = 0, nP = 0, nEnc = 0;
+#ifndef MADRL_WW_SKIP_EMPTY_CATCH
+#define MADRL_WW_SKIP_EMPTY_CATCH 0   // A/B candidate: one ballot skips the catch logic on steps without any collision
+#endif
+#if MADRL_WW_SKIP_EMPTY_CATCH
+        bool touched = false;
+#pragma unroll
+        for (int c = 0; c < OPL; ++c) touched |= col[c] != 0u;
+        if (__ballot_sync(FULL_MASK, touched) != 0u) {
+#endif
 #pragma unroll
         for (int c = 0; c < OPL; ++c) {
           const int cnt = __popc(col[c]);
@@ -445,6 +462,9 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
         whoE = __reduce_or_sync(FULL_MASK, whoE);
         whoP = __reduce_or_sync(FULL_MASK, whoP);
         whoEnc = __reduce_or_sync(FULL_MASK, whoEnc);
+#if MADRL_WW_SKIP_EMPTY_CATCH
+        }
+#endif
         // ww:411-428 tail of every pursuer's row: [touched an evader, touched a poison, id]; lane i
         // writes pursuer i's.  whoEnc / whoP are exactly the any-collision masks (ww:376, ww:293).
         if (lane < p.Np) {

@@ -49,7 +49,8 @@ class BatchedPursuitEvade(object):
     def __init__(self, n_envs, map_pool, n_evaders=1, n_pursuers=1, obs_range=3, flatten=True,
                  layer_norm=10, n_catch=2, catchr=0.01, term_pursuit=5.0, urgency_reward=0.0,
                  include_id=True, surround=True, constraint_window=1.0, sample_maps=False,
-                 reward_mech='global', device=None, seed=0, env_id_base=0, max_path_length=0):
+                 reward_mech='global', random_opponents=False, max_opponents=10, device=None, seed=0,
+                 env_id_base=0, max_path_length=0):
         if not torch.cuda.is_available():
             raise _lib.EngineError("madrl_b200 needs a CUDA device (there is no CPU fallback)")
         self._L = _lib.lib()
@@ -69,6 +70,7 @@ class BatchedPursuitEvade(object):
             flatten=int(bool(flatten)), n_catch=n_catch, surround=int(bool(surround)),
             reward_global=int(reward_mech == 'global'), include_id=int(bool(include_id)),
             sample_maps=int(bool(sample_maps)), max_path_length=int(max_path_length or 0),
+            max_opponents=int(max_opponents) if random_opponents else 0,   # pursuit_evade.py:81-82,177-181
             layer_norm=float(layer_norm), catchr=float(catchr), term_pursuit=float(term_pursuit),
             urgency_reward=float(urgency_reward), constraint_window=float(constraint_window),
             seed=int(seed))
@@ -205,9 +207,8 @@ class PursuitEvade(AbstractMAEnv, EzPickle):
         self.flatten = kw.pop('flatten', True)
         self.layer_norm = kw.pop('layer_norm', 10)
         self.n_catch = kw.pop('n_catch', 2)
-        if kw.pop('random_opponents', False):
-            raise NotImplementedError("random_opponents is not supported by the batched engine")
-        kw.pop('max_opponents', None)
+        self.random_opponents = kw.pop('random_opponents', False)      # pursuit_evade.py:81-82
+        self.max_opponents = kw.pop('max_opponents', 10)
         self.catchr = kw.pop('catchr', 0.01)
         self.caughtr = kw.pop('caughtr', -0.01)
         self.term_pursuit = kw.pop('term_pursuit', 5.0)
@@ -243,7 +244,8 @@ class PursuitEvade(AbstractMAEnv, EzPickle):
                     catchr=self.catchr, term_pursuit=self.term_pursuit,
                     urgency_reward=self.urgency_reward, include_id=self.include_id,
                     surround=self.surround, constraint_window=self.constraint_window,
-                    sample_maps=self.sample_maps, reward_mech=self._reward_mech)
+                    sample_maps=self.sample_maps, reward_mech=self._reward_mech,
+                    random_opponents=self.random_opponents, max_opponents=self.max_opponents)
 
     def setup(self):
         self.pursuers = [DiscreteAgent(self.obs_range, flatten=self.flatten) for _ in range(self.n_pursuers)]
@@ -275,6 +277,9 @@ class PursuitEvade(AbstractMAEnv, EzPickle):
         self._engine.set_params(self.catchr, self.constraint_window)
         obs = self._engine.reset().cpu().numpy().astype(np.float64)
         self._n_live = self.n_evaders
+        if self.random_opponents:      # this episode's evader count was drawn on the device (pursuit_evade.py:179)
+            gone = int(self._engine.state['gone'][0].item()) & ((1 << self.n_evaders) - 1)
+            self._n_live = self.n_evaders - bin(gone).count("1")
         return [self._shape(obs[0, i]) for i in range(self.n_pursuers)]
 
     def _shape(self, o):

@@ -106,6 +106,9 @@ PE_CASES = {
                                 catchr=0.1, sample_maps=False), 25, 3, 1500, 0),
     "pe_crowd": ("small5", dict(n_evaders=4, n_pursuers=10, obs_range=3, surround=True, reward_mech='local',
                                 catchr=0.1, term_pursuit=5.0, sample_maps=False), 27, 6, 600, 0),
+    "pe_random_opp": ("small5", dict(n_evaders=5, n_pursuers=6, obs_range=3, surround=False, n_catch=1,
+                                     reward_mech='local', catchr=0.1, random_opponents=True, max_opponents=6),
+                      28, 7, 400, 0),
     "pe_even_range": ("small5", dict(n_evaders=3, n_pursuers=3, obs_range=4, surround=False, n_catch=1,
                                      reward_mech='global'), 26, 4, 200, 0),
 }

@@ -25,7 +25,7 @@ class PursuitOracle(object):
     def __init__(self, map_pool, n_evaders=1, n_pursuers=1, obs_range=3, flatten=True,
                  layer_norm=10, n_catch=2, catchr=0.01, term_pursuit=5.0, urgency_reward=0.0,
                  include_id=True, surround=True, constraint_window=1.0, sample_maps=False,
-                 reward_mech='global', rng=None):
+                 reward_mech='global', random_opponents=False, max_opponents=10, rng=None):
         self.map_pool = np.asarray(map_pool)
         self.map = self.map_pool[0]
         self.xs, self.ys = self.map.shape
@@ -36,6 +36,7 @@ class PursuitOracle(object):
         self.include_id, self.surround = include_id, surround
         self.constraint_window, self.sample_maps = constraint_window, sample_maps
         self.reward_mech = reward_mech
+        self.random_opponents, self.max_opponents = random_opponents, max_opponents       # pe:81-82
         self.rng = rng if rng is not None else Stream(0, 0)
         self.local_obs = np.zeros((n_pursuers, 4, obs_range, obs_range))        # pe:119, never re-zeroed
         self.model_state = np.zeros((4,) + self.map.shape, dtype=np.float32)    # pe:152
@@ -71,6 +72,10 @@ class PursuitOracle(object):
     # ------------------------------------------------------------------ pe:173-207
     def reset(self):
         self.gone[:] = False
+        n_ev = self.Ne
+        if self.random_opponents:            # pe:177-181: this episode has 1 .. max_opponents-1 evaders;
+            n_ev = self.rng.randint(1, self.max_opponents)   # the draw precedes the map sample
+            self.gone[n_ev:] = True          # the others never exist (the reference rebuilds its lists)
         if self.sample_maps:
             self.map = self.map_pool[self.rng.randint(len(self.map_pool))]
         xws = self.rng.uniform(0.0, 1.0 - self.constraint_window)
@@ -79,11 +84,11 @@ class PursuitOracle(object):
         yl, yu = int(self.ys * yws), int(self.ys * (yws + self.constraint_window))
         for i in range(self.Np):
             self.ppos[i] = self._spawn(xl, xu, yl, yu)
-        for i in range(self.Ne):
+        for i in range(n_ev):
             self.epos[i] = self._spawn(xl, xu, yl, yu)
         self.model_state[0] = self.map
         self.model_state[1] = self._count_grid(self.ppos)
-        self.model_state[2] = self._count_grid(self.epos)
+        self.model_state[2] = self._count_grid(self.epos, ~self.gone)
         return self._collect_obs()
 
     # ------------------------------------------------------------------ pe:359-381

@@ -195,6 +195,7 @@ def make_reference_pursuit(map_pool, stream, **kwargs):
     pe_mod.np = proxy
     au_mod.np = proxy
     env = pe_mod.PursuitEvade(map_pool, evader_controller=StreamController(5, stream), **kwargs)
+    env.np_random = stream      # pursuit_evade.py:179 (random_opponents) draws from self.np_random
     return env
 
 

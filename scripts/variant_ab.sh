@@ -19,7 +19,7 @@ run() {  # name, lib-or-empty, families
       sed "s/^/$n: /" $O/sweep_${f}_$n.log >> $O/summary.log
     done )
 }
-run default "" ww,pe,hw
+run default "" ${DEFAULT_FAMS:-ww,pe,hw}
 for spec in "$@"; do
   v=${spec%%:*}; fams=${spec#*:}; [ "$fams" = "$spec" ] && fams=ww,pe,hw
   run $v $V/libmadrl_b200_$v.so $fams

@@ -47,7 +47,9 @@ if __name__ == "__main__":
         run(4096, 16, 4, 0, c4, reps=2)
     if which == "quick":
         run(4096, 256, 4, 0, c2)
+        run(4096, 256, 4, 0, c2)
         run(4096, 16, 4, 0, c4)
+        run(4096, 64, 4, 0, c4)
     if which in ("all", "c4"):
         run(4096, 16, 4, 0, c4)
         run(16384, 8, 4, 0, c4)

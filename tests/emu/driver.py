@@ -208,7 +208,8 @@ class EmuPursuit(_Engine):
     def __init__(self, n_envs, map_pool, n_evaders=1, n_pursuers=1, obs_range=3, flatten=True,
                  layer_norm=10, n_catch=2, catchr=0.01, term_pursuit=5.0, urgency_reward=0.0,
                  include_id=True, surround=True, constraint_window=1.0, sample_maps=False,
-                 reward_mech='global', seed=0, env_id_base=0, max_path_length=0, defines=()):
+                 reward_mech='global', random_opponents=False, max_opponents=10, seed=0, env_id_base=0,
+                 max_path_length=0, defines=()):
         self.lib = load(defines)
         mp = np.ascontiguousarray(np.asarray(map_pool), dtype=np.int32)
         if mp.ndim == 2:
@@ -221,6 +222,7 @@ class EmuPursuit(_Engine):
             flatten=int(bool(flatten)), n_catch=n_catch, surround=int(bool(surround)),
             reward_global=int(reward_mech == 'global'), include_id=int(bool(include_id)),
             sample_maps=int(bool(sample_maps)), max_path_length=int(max_path_length or 0),
+            max_opponents=int(max_opponents) if random_opponents else 0,
             layer_norm=float(layer_norm), catchr=float(catchr), term_pursuit=float(term_pursuit),
             urgency_reward=float(urgency_reward), constraint_window=float(constraint_window), seed=int(seed))
         self._finish((_p(mp),))
@@ -291,6 +293,8 @@ def _pe_facade(n_envs, map_pool, device=None, **kw):
         lib.madrl_pursuit_set_params.argtypes = [C.c_void_p, C.c_double, C.c_double]
         f.emu._check(lib.madrl_pursuit_set_params(f.emu._h, float(catchr), float(constraint_window)))
     f.set_params = set_params
+    import torch
+    type(f).state = property(lambda self: {'gone': torch.tensor([self.emu.state(e)['gone'] for e in range(self.n_envs)])})
     return f
 
 

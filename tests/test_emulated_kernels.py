@@ -205,6 +205,8 @@ PE = {
                               catchr=0.1, term_pursuit=5.0)),
     "conv_small": (small_map, dict(n_evaders=3, n_pursuers=3, obs_range=4, surround=False, n_catch=1,
                                    reward_mech='global', flatten=False)),
+    "random_opp": (small_map, dict(n_evaders=5, n_pursuers=6, obs_range=3, surround=False, n_catch=1,
+                                   reward_mech='local', catchr=0.1, random_opponents=True, max_opponents=6)),
 }
 
 
@@ -220,7 +222,8 @@ def check_pursuit_state(eng, oracles):
 
 @pytest.mark.parametrize("variant", PE_VARIANTS)
 @pytest.mark.parametrize("name,E,T", [("c3", 5, 40), ("c3_global", 3, 30), ("ncatch", 5, 40), ("window_r9", 5, 40),
-                                      ("many_evaders", 2, 12), ("crowd", 6, 120), ("conv_small", 6, 80)])
+                                      ("many_evaders", 2, 12), ("crowd", 6, 120), ("conv_small", 6, 80),
+                                      ("random_opp", 8, 60)])
 def test_pursuit_trajectories_bit_exact(variant, name, E, T):
     from emu.driver import EmuPursuit
     mk, cfg = PE[name]
@@ -248,9 +251,10 @@ def test_pursuit_trajectories_bit_exact(variant, name, E, T):
 
 
 @pytest.mark.parametrize("variant", PE_VARIANTS)
-def test_pursuit_auto_reset(variant):
+@pytest.mark.parametrize("name", ["crowd", "random_opp"])
+def test_pursuit_auto_reset(variant, name):
     from emu.driver import EmuPursuit
-    mk, cfg = PE["crowd"]
+    mk, cfg = PE[name]
     maps, E, T, mpl, seed = mk(), 5, 40, 9, 3
     eng = EmuPursuit(E, maps, seed=seed, max_path_length=mpl, defines=VARIANTS[variant], **cfg)
     eng.reset()
@@ -342,7 +346,7 @@ def test_waterworld_reproduces_reference_golden(variant, name):
 
 
 @pytest.mark.parametrize("variant", PE_VARIANTS)
-@pytest.mark.parametrize("name", ["pe_c3", "pe_c3_global", "pe_ncatch", "pe_window", "pe_small", "pe_even_range",
+@pytest.mark.parametrize("name", ["pe_c3", "pe_c3_global", "pe_ncatch", "pe_window", "pe_small", "pe_even_range", "pe_random_opp",
                                   "pe_crowd"])
 def test_pursuit_reproduces_reference_golden(variant, name):
     from emu.driver import EmuPursuit

@@ -51,6 +51,10 @@ CASES = {
     "conv_layout": (pool16, dict(C3, flatten=False, n_evaders=12, obs_range=5)),     # (R, R, 4) obs
     "conv_small": (small_map, dict(n_evaders=3, n_pursuers=3, obs_range=4, surround=False, n_catch=1,
                                    reward_mech='global', flatten=False)),
+    # random_opponents (pursuit_evade.py:81-82,177-181): 1..max_opponents-1 evaders per episode
+    "random_opp": (small_map, dict(n_evaders=5, n_pursuers=6, obs_range=3, surround=False, n_catch=1,
+                                   reward_mech='local', catchr=0.1, random_opponents=True, max_opponents=6)),
+    "random_opp_c3": (pool16, dict(C3, random_opponents=True, max_opponents=31)),
 }
 
 
@@ -76,7 +80,8 @@ def check_state(eng, oracles):
 @pytest.mark.parametrize("name,E,T", [("c3", 24, 120), ("c3_global", 8, 80), ("ncatch", 16, 120),
                                       ("window_r9", 16, 120), ("many_evaders", 4, 40),
                                       ("crowd", 48, 300), ("even_range", 32, 150),
-                                      ("conv_layout", 12, 100), ("conv_small", 16, 150)])
+                                      ("conv_layout", 12, 100), ("conv_small", 16, 150),
+                                      ("random_opp", 48, 200), ("random_opp_c3", 16, 60)])
 def test_trajectories_bit_exact(name, E, T):
     mk, cfg = CASES[name]
     maps = mk()
@@ -104,7 +109,7 @@ def test_trajectories_bit_exact(name, E, T):
 
 
 @pytest.mark.parametrize("name", ["pe_c3", "pe_c3_global", "pe_ncatch", "pe_window", "pe_small",
-                                  "pe_even_range", "pe_crowd"])
+                                  "pe_even_range", "pe_crowd", "pe_random_opp"])
 def test_matches_reference_golden(name):
     g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
     cfg = json.loads(str(g["config"]))
@@ -129,8 +134,9 @@ def test_matches_reference_golden(name):
     assert int(eng.state['rng_counter'][0].item()) == int(g["counter"])
 
 
-def test_auto_reset_and_horizon():
-    mk, cfg = CASES["crowd"]
+@pytest.mark.parametrize("name", ["crowd", "random_opp"])
+def test_auto_reset_and_horizon(name):
+    mk, cfg = CASES[name]
     maps = mk()
     E, T, mpl, seed = 12, 60, 17, 3
     eng = make(maps, cfg, E, seed=seed, max_path_length=mpl)

@@ -10,7 +10,7 @@ from conftest import GOLDEN_DIR, ROOT
 from oracle.philox import Stream
 from oracle.pursuit_oracle import PursuitOracle
 
-PE_GOLDEN = ["pe_c3", "pe_c3_global", "pe_ncatch", "pe_window", "pe_small", "pe_even_range", "pe_crowd"]
+PE_GOLDEN = ["pe_c3", "pe_c3_global", "pe_ncatch", "pe_window", "pe_small", "pe_even_range", "pe_crowd", "pe_random_opp"]
 
 
 def small_map():
@@ -59,6 +59,9 @@ def test_oracle_reproduces_golden(name):
     (dict(n_evaders=2, n_pursuers=4, obs_range=3, surround=True, reward_mech='local', catchr=0.1), 1500, 5, True),
     (dict(n_evaders=3, n_pursuers=3, obs_range=4, surround=False, n_catch=1, reward_mech='global',
           flatten=False), 300, 6, True),
+    # random_opponents (pursuit_evade.py:81-82,177-181): 1..max_opponents-1 evaders per episode
+    (dict(n_evaders=5, n_pursuers=6, obs_range=3, surround=False, n_catch=1, reward_mech='local', catchr=0.1,
+          random_opponents=True, max_opponents=6), 600, 8, True),
 ])
 def test_oracle_equals_reference_bitwise(kw, steps, seed, small):
     from oracle.refshim import make_reference_pursuit
