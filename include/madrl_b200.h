@@ -120,6 +120,12 @@ int madrl_ww_seed(madrl_ww* h, uint64_t seed, void* stream);
 /* Launch geometry override (0 = library default): resident blocks per SM.  Blocks are one warp (= one
  * env) since round 2; `warps_per_block` is accepted for ABI stability and ignored. */
 int madrl_ww_set_launch(madrl_ww* h, int warps_per_block, int blocks_per_sm);
+/* Terminal observations: with auto_reset the obs slot of a done step holds the RESET observation
+ * (VecEnvExecutor semantics); StandardizedEnv (madrl_environments/__init__.py:283-291) also sees the
+ * terminal one.  After this call every `*_rollout` (device pointers) with auto_reset first copies the rows
+ * of a finished env to the same [t][e] slot of term_obs_dev (same shape as that rollout's obs tensor;
+ * other slots are left untouched).  NULL switches it off. */
+int madrl_ww_set_terminal_obs(madrl_ww* h, void* term_obs_dev);
 /* Fused per-rollout exchange for env-sharded multi-GPU runs: after this call every rollout also
  * stores its reward / done / info rows into slot `slot` of each of the `n_dest` listed gather
  * buffers (peer-mapped device pointers: CUDA-IPC mappings of other ranks' buffers over NVLink; one
@@ -201,6 +207,12 @@ int madrl_pursuit_destroy(madrl_pursuit* h);
 void* madrl_pursuit_state_ptr(madrl_pursuit* h);
 int madrl_pursuit_seed(madrl_pursuit* h, uint64_t seed, void* stream);
 int madrl_pursuit_set_launch(madrl_pursuit* h, int warps_per_block, int blocks_per_sm);
+/* Terminal observations: with auto_reset the obs slot of a done step holds the RESET observation
+ * (VecEnvExecutor semantics); StandardizedEnv (madrl_environments/__init__.py:283-291) also sees the
+ * terminal one.  After this call every `*_rollout` (device pointers) with auto_reset first copies the rows
+ * of a finished env to the same [t][e] slot of term_obs_dev (same shape as that rollout's obs tensor;
+ * other slots are left untouched).  NULL switches it off. */
+int madrl_pursuit_set_terminal_obs(madrl_pursuit* h, void* term_obs_dev);
 /* Curriculum knobs that survive pickling in the reference (pursuit_evade.py:264-272,397-411). */
 int madrl_pursuit_set_params(madrl_pursuit* h, double catchr, double constraint_window);
 /* reset(): obs_dev float [E][Np][obs_dim]. */
@@ -254,6 +266,12 @@ int madrl_hostage_destroy(madrl_hostage* h);
 void* madrl_hostage_state_ptr(madrl_hostage* h);
 int madrl_hostage_seed(madrl_hostage* h, uint64_t seed, void* stream);
 int madrl_hostage_set_launch(madrl_hostage* h, int warps_per_block, int blocks_per_sm);
+/* Terminal observations: with auto_reset the obs slot of a done step holds the RESET observation
+ * (VecEnvExecutor semantics); StandardizedEnv (madrl_environments/__init__.py:283-291) also sees the
+ * terminal one.  After this call every `*_rollout` (device pointers) with auto_reset first copies the rows
+ * of a finished env to the same [t][e] slot of term_obs_dev (same shape as that rollout's obs tensor;
+ * other slots are left untouched).  NULL switches it off. */
+int madrl_hostage_set_terminal_obs(madrl_hostage* h, void* term_obs_dev);
 /* obs_dev real [E][n_good][obs_dim] */
 int madrl_hostage_reset(madrl_hostage* h, const uint8_t* mask_dev, void* obs_dev, void* stream);
 /* actions_dev real [T][E][n_good][2]; obs_dev real [T][E][n_good][obs_dim]; rew_dev real
@@ -290,6 +308,14 @@ int madrl_frame_stack_f32(int T, int E, int A, int D, int B, const float* obs_de
 int madrl_standardize_f32(int T, size_t n, float* x_dev, double* mean_dev, double* var_dev,
                           double alpha, double eps, int center, double scale, int enable,
                           void* stream);
+/* Same, for observations of an auto-reset rollout with the terminal observations kept on the side
+ * (madrl_*_set_terminal_obs): at a step with done[t][e] set, the running estimate of env e's columns is
+ * first updated with term[t] (which is standardised in place too) and then with x[t] -- the reference
+ * order: step() standardises the terminal observation, reset() the first one of the next episode.
+ * x, term [T][E][per_env]; done uint8 [T][E]; mean, var float64 [E][per_env]. */
+int madrl_standardize_obs_terminal_f32(int T, int E, size_t per_env, float* x_dev, float* term_dev,
+                                       const uint8_t* done_dev, double* mean_dev, double* var_dev,
+                                       double alpha, double eps, void* stream);
 /* DiagnosticsWrapper episode statistics (madrl_environments/__init__.py:314-369): rew [T][E][A],
  * done uint8 [T][E]; carry float64 [E][A+3] (zero-initialised by the caller, kept between calls);
  * outputs at the steps where an episode closes (ep_end[t][e] = 1; zeros elsewhere):

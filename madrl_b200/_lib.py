@@ -109,6 +109,7 @@ def _declare(lib):
     lib.madrl_ww_state_ptr.restype = vp
     lib.madrl_ww_seed.argtypes = [vp, u64, vp]
     lib.madrl_ww_set_launch.argtypes = [vp, i32, i32]
+    lib.madrl_ww_set_terminal_obs.argtypes = [vp, vp]
     lib.madrl_ww_set_peers.argtypes = [vp, i32, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.madrl_ww_reset.argtypes = [vp, vp, vp, vp]
     lib.madrl_ww_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp]
@@ -121,6 +122,7 @@ def _declare(lib):
     lib.madrl_standardize_f32.argtypes = [i32, C.c_size_t, vp, vp, vp, C.c_double, C.c_double, i32,
                                           C.c_double, i32, vp]
     lib.madrl_episode_stats_f32.argtypes = [i32, i32, i32, vp, vp, C.c_double, i32, vp, vp, vp, vp, vp, vp]
+    lib.madrl_standardize_obs_terminal_f32.argtypes = [i32, i32, C.c_size_t, vp, vp, vp, vp, vp, C.c_double, C.c_double, vp]
     lib.madrl_paths_plan.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.madrl_paths_pack_u32.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.madrl_moments_f32.argtypes = [C.c_size_t, vp, vp, vp, vp, vp]
@@ -132,6 +134,7 @@ def _declare(lib):
     lib.madrl_hostage_state_ptr.restype = vp
     lib.madrl_hostage_seed.argtypes = [vp, u64, vp]
     lib.madrl_hostage_set_launch.argtypes = [vp, i32, i32]
+    lib.madrl_hostage_set_terminal_obs.argtypes = [vp, vp]
     lib.madrl_hostage_reset.argtypes = [vp, vp, vp, vp]
     lib.madrl_hostage_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp]
     lib.madrl_hostage_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
@@ -145,6 +148,7 @@ def _declare(lib):
     lib.madrl_pursuit_state_ptr.restype = vp
     lib.madrl_pursuit_seed.argtypes = [vp, u64, vp]
     lib.madrl_pursuit_set_launch.argtypes = [vp, i32, i32]
+    lib.madrl_pursuit_set_terminal_obs.argtypes = [vp, vp]
     lib.madrl_pursuit_set_params.argtypes = [vp, C.c_double, C.c_double]
     lib.madrl_pursuit_reset.argtypes = [vp, vp, vp, vp]
     lib.madrl_pursuit_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp]

@@ -139,6 +139,17 @@ template <> struct CandSlot<double> {
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #endif  // MADRL_EMU_PTX_HELPERS
 
+// StandardizedEnv sees the TERMINAL observation of an episode before the reset one
+// (madrl_environments/__init__.py:283-291 step(), then reset()); under auto-reset the rollout's obs slot is
+// overwritten by the reset observation, so -- when the caller asked for it -- the rows of a finished env
+// are first copied to the same slot of a side tensor.  Executed by one warp on done steps only.
+template <typename T>
+__device__ __forceinline__ void keep_terminal_rows(const T* src, T* dst, int n, int lane) {
+  __syncwarp();                                   // the rows were stored by other lanes of this warp
+  for (int i = lane; i < n; i += 32) dst[i] = __ldcg(src + i);
+  __syncwarp();                                   // ... and the reset pass overwrites them next
+}
+
 template <typename real>
 __device__ __forceinline__ real clip01(real x) {
   return x < (real)0 ? (real)0 : (x > (real)1 ? (real)1 : x);

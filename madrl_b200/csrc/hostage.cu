@@ -44,6 +44,7 @@ struct HWParams {
   uint8_t* done;
   int32_t* info;     // [T][E][2] = (ho_saved, cr_encs)
   const uint8_t* mask;
+  real* term_obs;    // optional [T][E][Nr][D]: terminal observations of done steps (see keep_terminal_rows)
 };
 
 template <typename real> struct HVec2;
@@ -394,6 +395,8 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
             reinterpret_cast<int2*>(p.info)[te] = make_int2(nH, nC);
           }
           need_reset = done && p.auto_reset;
+          if (need_reset && p.term_obs != nullptr)
+            keep_terminal_rows(obs_t - lane, p.term_obs + ((obs_t - lane) - p.obs), p.Nr * p.D, lane);
         }
         pass = need_reset ? 1 : 0;
       } while (need_reset);
@@ -432,6 +435,7 @@ struct madrl_hostage {
   int device, sms;
   int warps_per_block, blocks_per_sm;
   madrl::HostPipe pipe;   // staging + streams of the host-buffer entry points (lazily created)
+  void* term_obs;         // madrl_hostage_set_terminal_obs (NULL = off)
 };
 
 static int hw_validate(const madrl_hostage_config* c) {
@@ -531,6 +535,12 @@ extern "C" int madrl_hostage_seed(madrl_hostage* h, uint64_t seed, void* stream)
   return MADRL_OK;
 }
 
+extern "C" int madrl_hostage_set_terminal_obs(madrl_hostage* h, void* term_obs_dev) {
+  MADRL_REQUIRE(h != nullptr, "handle is NULL");
+  h->term_obs = term_obs_dev;
+  return MADRL_OK;
+}
+
 extern "C" int madrl_hostage_set_launch(madrl_hostage* h, int warps_per_block, int blocks_per_sm) {
   MADRL_REQUIRE(h != nullptr, "handle is NULL");
   MADRL_REQUIRE(warps_per_block >= 0 && warps_per_block <= 4, "warps_per_block must be in [0,4]");
@@ -597,6 +607,7 @@ static int hw_launch(madrl_hostage* h, int mode, int T, const void* actions, voi
   p.ctr = (uint64_t*)(st + h->lay.rng_counter); p.sensors = (const real*)(st + h->lay.sensors);
   p.actions = (const real*)actions; p.obs = (real*)obs; p.rew = (real*)rew;
   p.done = done; p.info = info; p.mask = mask;
+  p.term_obs = (mode == 0) ? (real*)h->term_obs : nullptr;
   const int opl = (p.Nall - p.Nr + 31) / 32, kch = (p.K + 31) / 32;
 #define MADRL_HW_CASE(O, KH, KC_) return hw_launch_inst<real, O, KH, KC_>(h, p, stream)
   if (p.K == 30) {
@@ -668,11 +679,15 @@ extern "C" int madrl_hostage_rollout_host2(madrl_hostage* h, int T, const void* 
   MADRL_REQUIRE((flags & ~MADRL_HOST_OBS_LAST) == 0, "unknown flags %d", flags);
   const size_t E = h->cfg.n_envs, Nr = h->cfg.n_good, rb = h->lay.real_bytes;
   const StepBytes sb = {E * Nr * 2 * rb, E * Nr * h->lay.obs_dim * rb, E * Nr * rb, E, E * 2 * 4};
-  return host_rollout(h->pipe, T, sb, actions_host, obs_host, rew_host, done_host, info_host,
+  void* const keep = h->term_obs;    // chunk-relative offsets: the side tensor is a device-API feature
+  h->term_obs = nullptr;
+  const int rc_ = host_rollout(h->pipe, T, sb, actions_host, obs_host, rew_host, done_host, info_host,
                       flags & MADRL_HOST_OBS_LAST,
                       [&](int, int Tc, char* a, char* o, char* r, char* d, char* i, cudaStream_t st) {
                         return madrl_hostage_rollout(h, Tc, a, o, r, (uint8_t*)d, (int32_t*)i, auto_reset, st);
                       });
+  h->term_obs = keep;
+  return rc_;
 }
 
 extern "C" int madrl_hostage_rollout_host(madrl_hostage* h, int T, const void* actions_host, void* obs_host,

@@ -94,6 +94,35 @@ __global__ void standardize_kernel(int T, size_t n, float* __restrict__ x, doubl
   var[i] = v;
 }
 
+// Observation standardiser for auto-reset rollouts with the terminal observations on the side.
+__global__ void standardize_terminal_kernel(int T, int E, size_t per_env, float* __restrict__ x,
+                                            float* __restrict__ term, const uint8_t* __restrict__ done,
+                                            double* __restrict__ mean, double* __restrict__ var, double alpha,
+                                            double eps) {
+  const size_t n = (size_t)E * per_env;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t e = i / per_env;
+  double m = mean[i], v = var[i];
+  for (int t = 0; t < T; ++t) {
+    const size_t k = (size_t)t * n + i;
+    if (done[(size_t)t * E + e]) {                 // step(): the terminal observation comes first
+      const double tv = (double)term[k];
+      m = (1.0 - alpha) * m + alpha * tv;
+      const double d = tv - m;
+      v = (1.0 - alpha) * v + alpha * d * d;
+      term[k] = (float)((tv - m) / (sqrt(v) + eps));
+    }
+    const double xv = (double)x[k];
+    m = (1.0 - alpha) * m + alpha * xv;
+    const double d = xv - m;
+    v = (1.0 - alpha) * v + alpha * d * d;
+    x[k] = (float)((xv - m) / (sqrt(v) + eps));
+  }
+  mean[i] = m;
+  var[i] = v;
+}
+
 // DiagnosticsWrapper episode statistics (madrl_environments/__init__.py:314-369): per env, walk the
 // time axis accumulating the per-agent episode reward, the episode length and the discounted return
 // of the agent-mean reward; an episode closes where done[t] is set or its length reaches
@@ -411,6 +440,19 @@ extern "C" int madrl_paths_pack_u32(int T, int E, int A, int D, const void* src_
   MADRL_REQUIRE(blocks < ((size_t)1 << 31), "too many rows for one launch");
   MADRL_LAUNCH(paths_pack_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, T, E, A, D, (const uint32_t*)src_dev,
                (const uint32_t*)first_dev, seg_start_dev, seg_len_dev, (uint32_t*)dst_dev);
+  g_launches.fetch_add(1);
+  MADRL_CUDA_CHECK(cudaGetLastError());
+  return MADRL_OK;
+}
+
+extern "C" int madrl_standardize_obs_terminal_f32(int T, int E, size_t per_env, float* x_dev, float* term_dev,
+                                                  const uint8_t* done_dev, double* mean_dev, double* var_dev,
+                                                  double alpha, double eps, void* stream) {
+  MADRL_REQUIRE(T >= 1 && E >= 1 && per_env >= 1, "bad sizes");
+  MADRL_REQUIRE(x_dev && term_dev && done_dev && mean_dev && var_dev, "NULL buffer");
+  const size_t n = (size_t)E * per_env;
+  MADRL_LAUNCH(standardize_terminal_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, T, E, per_env,
+               x_dev, term_dev, done_dev, mean_dev, var_dev, alpha, eps);
   g_launches.fetch_add(1);
   MADRL_CUDA_CHECK(cudaGetLastError());
   return MADRL_OK;

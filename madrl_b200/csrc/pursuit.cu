@@ -54,6 +54,7 @@ struct PEParams {
   uint8_t* done;                  // [T][E]
   int32_t* info;                  // [T][E]  removed
   const uint8_t* mask;
+  float* term_obs;                // optional [T][E][Np][D]: terminal observations of done steps
 };
 
 // float64 `ndarray.mean()` exactly as NumPy (>= 1.22, checked against 2.3.5) computes it for a
@@ -387,6 +388,8 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
             p.info[te] = removed;
           }
           need_reset = done && p.auto_reset;   // VecEnvExecutor.step (vec_env_executor.py:24-27)
+          if (need_reset && p.term_obs != nullptr)
+            keep_terminal_rows(obs_t, p.term_obs + (obs_t - p.obs), Np * p.D, lane);
         }
         pass = need_reset ? 1 : 0;
       } while (need_reset);
@@ -428,6 +431,7 @@ struct madrl_pursuit {
   int device, sms;
   int warps_per_block, blocks_per_sm;
   madrl::HostPipe pipe;   // staging + streams of the host-buffer entry points (lazily created)
+  void* term_obs;         // madrl_pursuit_set_terminal_obs (NULL = off)
 };
 
 static int pe_validate(const madrl_pursuit_config* c) {
@@ -529,6 +533,12 @@ extern "C" int madrl_pursuit_seed(madrl_pursuit* h, uint64_t seed, void* stream)
   return MADRL_OK;
 }
 
+extern "C" int madrl_pursuit_set_terminal_obs(madrl_pursuit* h, void* term_obs_dev) {
+  MADRL_REQUIRE(h != nullptr, "handle is NULL");
+  h->term_obs = term_obs_dev;
+  return MADRL_OK;
+}
+
 extern "C" int madrl_pursuit_set_launch(madrl_pursuit* h, int warps_per_block, int blocks_per_sm) {
   MADRL_REQUIRE(h != nullptr, "handle is NULL");
   MADRL_REQUIRE(warps_per_block >= 0 && warps_per_block <= 4, "warps_per_block must be in [0,4]");
@@ -592,6 +602,7 @@ static int pe_launch(madrl_pursuit* h, int mode, int T, const int32_t* actions, 
   p.map_id = (int32_t*)(st + h->lay.map_id); p.path_len = (int32_t*)(st + h->lay.path_len);
   p.ctr = (uint64_t*)(st + h->lay.rng_counter); p.stale = (uint16_t*)(st + h->lay.stale);
   p.actions = actions; p.obs = obs; p.rew = rew; p.done = done; p.info = info; p.mask = mask;
+  p.term_obs = (mode == 0) ? (float*)h->term_obs : nullptr;
   const int epl = (p.Ne + 31) / 32, cpl = (RR + 31) / 32;
 #define MADRL_PE_CASE(EP, CP, RC_) return pe_launch_inst<EP, CP, RC_>(h, p, stream)
   if (p.R == 7) { if (epl == 1) MADRL_PE_CASE(1, 2, 7); MADRL_PE_CASE(2, 2, 7); }
@@ -650,12 +661,16 @@ extern "C" int madrl_pursuit_rollout_host2(madrl_pursuit* h, int T, const int32_
   MADRL_REQUIRE((flags & ~MADRL_HOST_OBS_LAST) == 0, "unknown flags %d", flags);
   const size_t E = h->cfg.n_envs, Np = h->cfg.n_pursuers;
   const StepBytes sb = {E * Np * 4, E * Np * h->lay.obs_dim * 4, E * Np * 4, E, E * 4};
-  return host_rollout(h->pipe, T, sb, actions_host, obs_host, rew_host, done_host, info_host,
+  void* const keep = h->term_obs;    // chunk-relative offsets: the side tensor is a device-API feature
+  h->term_obs = nullptr;
+  const int rc_ = host_rollout(h->pipe, T, sb, actions_host, obs_host, rew_host, done_host, info_host,
                       flags & MADRL_HOST_OBS_LAST,
                       [&](int, int Tc, char* a, char* o, char* r, char* d, char* i, cudaStream_t st) {
                         return madrl_pursuit_rollout(h, Tc, (const int32_t*)a, (float*)o, (float*)r, (uint8_t*)d,
                                                      (int32_t*)i, auto_reset, st);
                       });
+  h->term_obs = keep;
+  return rc_;
 }
 
 extern "C" int madrl_pursuit_rollout_host(madrl_pursuit* h, int T, const int32_t* actions_host, float* obs_host,

@@ -58,6 +58,7 @@ struct WWParams {
   uint8_t* done;
   int32_t* info;
   const uint8_t* mask;
+  real* term_obs;   // optional [T][E][A][D]: terminal observations of done steps (see keep_terminal_rows)
   // fused per-rollout exchange (multi-GPU): every rank also stores its reward / done / info rows
   // into slot `peer_rank` of each destination gather buffer through NVLink peer mappings (CUDA
   // IPC).  Rows are staged in registers and written as coalesced runs (rewards every 32/Np steps,
@@ -128,18 +129,18 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
   const int warp_stride = gridDim.x;
   const int eLo = p.Np, eHi = p.Np + p.Ne, Nall = p.Nall;
   constexpr bool SMEM = OPL >= 2;
-  constexpr bool ACT_PIPE = OPL <= 2;   // next step's action double-buffered in registers
   extern __shared__ __align__(16) unsigned char ww_smem[];
   // this warp's candidate slots (32-bit shared address)
   const uint32_t slots = SMEM ? smem_addr(ww_smem) : 0u;
 
   // ---- per-lane constants: this lane as OBJECT (classes, thresholds) and as SENSOR -----------
-  real coll2_l[OPL];
+  real cull2_l[OPL], coll2_l[OPL];
   unsigned mE[OPL], mP[OPL], mU[OPL];  // warp-uniform class masks of each object chunk
 #pragma unroll
   for (int c = 0; c < OPL; ++c) {
     const int o = lane + 32 * c;
     const bool isU = o < eLo, isE = o >= eLo && o < eHi, isP = o >= eHi && o < Nall;
+    cull2_l[c] = (o < Nall) ? p.cull2 : (real)-1;
     coll2_l[c] = isE ? p.coll2_e : (isP ? p.coll2_po : (real)-1);
     mU[c] = __ballot_sync(FULL_MASK, isU);
     mE[c] = __ballot_sync(FULL_MASK, isE);
@@ -166,10 +167,8 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     for (int c = 0; c < OPL; ++c) {
       const int o = lane + 32 * c;
       const bool v = o < Nall;
-      // lanes beyond the last object sit far outside every range test (never written back), so the
-      // cull / collision thresholds need no per-lane validity term
-      x[c] = v ? rec[o] : (real)1e15;
-      y[c] = v ? rec[Nall + o] : (real)1e15;
+      x[c] = v ? rec[o] : (real)0;
+      y[c] = v ? rec[Nall + o] : (real)0;
       vx[c] = v ? rec[2 * Nall + o] : (real)0;
       vy[c] = v ? rec[3 * Nall + o] : (real)0;
       col[c] = 0u;
@@ -184,9 +183,6 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     size_t te = (size_t)e;   // index of (t, e) in the [T][E] done / info tensors
     int pass = (p.mode == 1) ? 1 : 0;  // pass 1 = reset pass: fresh draws, zero action, obs only
     const V2* act_t = reinterpret_cast<const V2*>(p.actions) + (size_t)e * p.Np + lane;
-    V2 act_nx;
-    act_nx.x = 0; act_nx.y = 0;
-    if (ACT_PIPE && p.mode == 0 && lane < p.Np) act_nx = *act_t;
 
     // staging registers of the fused exchange
     const int rew_per = 32 / p.Np;                       // steps per coalesced reward run
@@ -198,14 +194,11 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     int sc_rew = 0;
 
     for (int t = 0; t < p.T; ++t) {
-      // this step's action was loaded one step ago; the load of the next one is issued now and is
-      // consumed ~800 instructions later (the FMUL behind a just-in-time load was the kernel's top stall)
-      V2 act = act_nx;
-      if (ACT_PIPE) {
-        if (p.mode == 0 && lane < p.Np && t + 1 < p.T) act_nx = act_t[p.agent_step];
-      } else if (p.mode == 0 && lane < p.Np) {   // big configurations: no registers to spare, latency is hidden anyway
+      V2 act;
+      act.x = 0; act.y = 0;
+      if (p.mode == 0 && lane < p.Np) {
         act = *act_t;
-        if (t + 1 < p.T) prefetch_l1(act_t + p.agent_step);
+        if (t + 1 < p.T) prefetch_l1(act_t + p.agent_step);   // next step's action -> L1
       }
       bool need_reset;
       do {
@@ -281,26 +274,26 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
           }
           if constexpr (SMEM) {
             constexpr uint32_t S = CandSlot<real>::kStride;
-            // slot = rank among the candidates in ascending object index; classes are contiguous in
-            // object index, so the class boundaries in slot order are cumulative counts
-            uint32_t nU = 0u, nUE = 0u, top = 0u;
+            uint32_t endU = slots, nEc = 0u, nPc = 0u, top = slots;
 #pragma unroll
             for (int c = 0; c < OPL; ++c) {
               // lanes as OBJECTS: geometry, collisions (ww:278-293), conservative range cull, staging
               const real rx = x[c] - mx, ry = y[c] - my;
               const real d2 = rx * rx + ry * ry;
-              const bool near = d2 <= p.cull2 && !(c == 0 && lane == pi);   // ww:70-71 `same`
+              const bool near = d2 <= cull2_l[c] && !(c == 0 && lane == pi);   // ww:70-71 `same`
               const unsigned cm = __ballot_sync(FULL_MASK, near);
               const bool hit = d2 <= coll2_l[c];
               if (hit) col[c] |= 1u << pi;
-              if (near) CandSlot<real>::put(slots + (top + (uint32_t)__popc(cm & lanemask_lt())) * S, rx, ry, d2, vx[c], vy[c]);
-              if (c == 0) nU = (uint32_t)__popc(cm & mU[0]);   // pursuers live in chunk 0 (Np <= 32)
-              nUE += (uint32_t)__popc(cm & (mU[c] | mE[c]));
-              top += (uint32_t)__popc(cm);
+              // slot = rank among the candidates in ascending object index (= lane + 32 c)
+              if (near) CandSlot<real>::put(top + (uint32_t)__popc(cm & ((1u << lane) - 1u)) * S, rx, ry, d2, vx[c], vy[c]);
+              if (c == 0) endU = slots + (uint32_t)__popc(cm & mU[0]) * S;   // pursuers live in chunk 0 (Np <= 32)
+              nEc += (uint32_t)__popc(cm & mE[c]);
+              nPc += (uint32_t)__popc(cm & mP[c]);
+              top += (uint32_t)__popc(cm) * S;
             }
             __syncwarp();
-            // lanes as SENSORS: slot order is U, E, P
-            const uint32_t endU = slots + nU * S, endE = slots + nUE * S, endP = slots + top * S;
+            // lanes as SENSORS: classes are contiguous in object index, hence in slot order U, E, P
+            const uint32_t endE = endU + nEc * S, endP = endE + nPc * S;
             const real up = p.range_up;   // `sv < up` <=> `sv <= range`; a best below `up` <=> sensed
             uint32_t aE[KCH], aP[KCH], aU[KCH];
 #pragma unroll
@@ -357,7 +350,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
             // lanes as OBJECTS: geometry, collisions (ww:278-293), conservative range cull
             const real rx = x[c] - mx, ry = y[c] - my;
             const real d2 = rx * rx + ry * ry;
-            unsigned cm = __ballot_sync(FULL_MASK, d2 <= p.cull2);
+            unsigned cm = __ballot_sync(FULL_MASK, d2 <= cull2_l[c]);
             if (c == 0) cm &= ~(1u << pi);  // ww:70-71 `same`
             const bool hit = d2 <= coll2_l[c];
             if (hit) col[c] |= 1u << pi;
@@ -427,15 +420,6 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
         // ---- catches, respawn, rewards: ww:285,293,358-385 -----------------------------------------
         unsigned whoE = 0u, whoP = 0u, whoEnc = 0u;
         int nE = 0, nP = 0, nEnc = 0;
-#ifndef MADRL_WW_SKIP_EMPTY_CATCH
-#define MADRL_WW_SKIP_EMPTY_CATCH 0   // A/B candidate: one ballot skips the catch logic on steps without any collision
-#endif
-#if MADRL_WW_SKIP_EMPTY_CATCH
-        bool touched = false;
-#pragma unroll
-        for (int c = 0; c < OPL; ++c) touched |= col[c] != 0u;
-        if (__ballot_sync(FULL_MASK, touched) != 0u) {
-#endif
 #pragma unroll
         for (int c = 0; c < OPL; ++c) {
           const int cnt = __popc(col[c]);
@@ -462,9 +446,6 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
         whoE = __reduce_or_sync(FULL_MASK, whoE);
         whoP = __reduce_or_sync(FULL_MASK, whoP);
         whoEnc = __reduce_or_sync(FULL_MASK, whoEnc);
-#if MADRL_WW_SKIP_EMPTY_CATCH
-        }
-#endif
         // ww:411-428 tail of every pursuer's row: [touched an evader, touched a poison, id]; lane i
         // writes pursuer i's.  whoEnc / whoP are exactly the any-collision masks (ww:376, ww:293).
         if (lane < p.Np) {
@@ -530,6 +511,8 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
           // VecEnvExecutor.step: a done env is reset in place and its obs slot receives the
           // reset observation (rllab/sandbox/rocky/tf/envs/vec_env_executor.py:24-27)
           need_reset = done && p.auto_reset;
+          if (need_reset && p.term_obs != nullptr)
+            keep_terminal_rows(obs_t - lane, p.term_obs + ((obs_t - lane) - p.obs), p.Np * p.D, lane);
         }
         pass = need_reset ? 1 : 0;
       } while (need_reset);
@@ -570,6 +553,7 @@ struct madrl_ww {
   int device, sms;
   int warps_per_block, blocks_per_sm;
   madrl::HostPipe pipe;   // staging + streams of the host-buffer entry points (lazily created)
+  void* term_obs;         // madrl_ww_set_terminal_obs (NULL = off)
   // peer gather buffers (multi-GPU fused exchange); n_peers == 0: disabled
   int n_peers, peer_rank, peer_tmax;
   void* peer_rew[8];
@@ -697,6 +681,12 @@ extern "C" int madrl_ww_set_peers(madrl_ww* h, int n_peers, int rank, int t_max,
   return MADRL_OK;
 }
 
+extern "C" int madrl_ww_set_terminal_obs(madrl_ww* h, void* term_obs_dev) {
+  MADRL_REQUIRE(h != nullptr, "handle is NULL");
+  h->term_obs = term_obs_dev;
+  return MADRL_OK;
+}
+
 extern "C" int madrl_ww_set_launch(madrl_ww* h, int warps_per_block, int blocks_per_sm) {
   MADRL_REQUIRE(h != nullptr, "handle is NULL");
   MADRL_REQUIRE(warps_per_block >= 0 && warps_per_block <= 4, "warps_per_block must be in [0,4]");
@@ -786,6 +776,7 @@ static int ww_launch(madrl_ww* h, int mode, int T, const void* actions, void* ob
   p.sensors = (const real*)(st + h->lay.sensors);
   p.actions = (const real*)actions; p.obs = (real*)obs; p.rew = (real*)rew;
   p.done = done; p.info = info; p.mask = mask;
+  p.term_obs = (mode == 0) ? (real*)h->term_obs : nullptr;
   p.n_peers = (mode == 0) ? h->n_peers : 0;
   p.peer_rank = h->peer_rank;
   if (p.n_peers > 0) {
@@ -873,11 +864,15 @@ extern "C" int madrl_ww_rollout_host2(madrl_ww* h, int T, const void* actions_ho
   MADRL_REQUIRE((flags & ~MADRL_HOST_OBS_LAST) == 0, "unknown flags %d", flags);
   const size_t E = h->cfg.n_envs, Np = h->cfg.n_pursuers, rb = h->lay.real_bytes;
   const StepBytes sb = {E * Np * 2 * rb, E * Np * h->lay.obs_dim * rb, E * Np * rb, E, E * 2 * 4};
-  return host_rollout(h->pipe, T, sb, actions_host, obs_host, rew_host, done_host, info_host,
+  void* const keep = h->term_obs;    // chunk-relative offsets: the side tensor is a device-API feature
+  h->term_obs = nullptr;
+  const int rc_ = host_rollout(h->pipe, T, sb, actions_host, obs_host, rew_host, done_host, info_host,
                       flags & MADRL_HOST_OBS_LAST,
                       [&](int, int Tc, char* a, char* o, char* r, char* d, char* i, cudaStream_t st) {
                         return madrl_ww_rollout(h, Tc, a, o, r, (uint8_t*)d, (int32_t*)i, auto_reset, st);
                       });
+  h->term_obs = keep;
+  return rc_;
 }
 
 extern "C" int madrl_ww_rollout_host(madrl_ww* h, int T, const void* actions_host, void* obs_host,

@@ -115,9 +115,11 @@ class FrameStack(object):
 class Standardizer(object):
     """StandardizedEnv's running observation / reward normalisation for a whole env batch
     (one running estimate per env, agent and observation coordinate, as each reference env keeps
-    its own).  Deviation from the wrapped-single-env reference under auto-reset: the terminal
-    observation of an episode is replaced by the reset observation in the rollout tensor, so the
-    running estimate sees the reset observation only (the reference updates on both)."""
+    its own).  Under auto-reset the rollout's obs slot of a done step holds the reset observation; the
+    reference's estimate also sees the terminal one (step() standardises it, then reset() the new
+    one, madrl_environments/__init__.py:283-291).  Pass `done` and the `terminal_obs` side tensor
+    (`engine.set_terminal_obs`) to `obs()` to reproduce that order exactly; without them the estimate
+    sees the reset observation only."""
 
     def __init__(self, n_envs, n_agents, obs_dim, device, scale_reward=1., enable_obsnorm=False,
                  enable_rewnorm=False, obs_alpha=0.001, rew_alpha=0.001, eps=1e-8):
@@ -128,12 +130,21 @@ class Standardizer(object):
         self.rew_mean = torch.zeros((n_envs, n_agents), dtype=torch.float64, device=device)
         self.rew_var = torch.ones((n_envs, n_agents), dtype=torch.float64, device=device)
 
-    def obs(self, obs):
-        """In place on obs [T,E,A,D] (or [E,A,D])."""
+    def obs(self, obs, done=None, terminal_obs=None):
+        """In place on obs [T,E,A,D] (or [E,A,D]); with `done` [T,E] and `terminal_obs` [T,E,A,D] the
+        terminal observations update the estimate first (and are standardised in place as well)."""
         if not self.enable_obsnorm:
             return obs
         x = obs if obs.dim() == 4 else obs.unsqueeze(0)
         assert x.is_contiguous()
+        if terminal_obs is not None:
+            assert done is not None and terminal_obs.shape == x.shape and terminal_obs.is_contiguous()
+            E = x.shape[1]
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.lib().madrl_standardize_obs_terminal_f32(
+                    x.shape[0], E, self.obs_mean.numel() // E, _ptr(x), _ptr(terminal_obs), _ptr(done.contiguous()),
+                    _ptr(self.obs_mean), _ptr(self.obs_var), self.obs_alpha, self.eps, _stream(x.device)))
+            return obs
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().madrl_standardize_f32(x.shape[0], self.obs_mean.numel(), _ptr(x),
                                                         _ptr(self.obs_mean), _ptr(self.obs_var), self.obs_alpha,

@@ -108,6 +108,16 @@ class BatchedPursuitEvade(object):
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def set_terminal_obs(self, term_obs):
+        """Keep the terminal observations of done steps: `term_obs` (same shape / dtype as the obs tensor
+        of the following auto-reset rollouts) receives, at the [t, e] slots where `done` is set, the
+        observation the env returned BEFORE it was reset in place (StandardizedEnv needs it,
+        madrl_environments/__init__.py:283-291).  None switches it off."""
+        if term_obs is not None:
+            assert term_obs.is_contiguous() and term_obs.device == self.device, "term_obs must be a contiguous device tensor"
+        self._term_keepalive = term_obs
+        _lib.check(self._L.madrl_pursuit_set_terminal_obs(self._h, _ptr(term_obs)))
+
     def set_launch(self, warps_per_block=0, blocks_per_sm=0):
         _lib.check(self._L.madrl_pursuit_set_launch(self._h, warps_per_block, blocks_per_sm))
 

@@ -176,6 +176,7 @@ static inline double __dmul_rn(double a, double b) { volatile double x = a, y = 
 static inline double __ddiv_rn(double a, double b) { volatile double x = a, y = b; return x / y; }
 template <typename T> static inline void __stcs(T* p, T v) { *p = v; }
 template <typename T> static inline T __ldcs(const T* p) { return *p; }
+template <typename T> static inline T __ldcg(const T* p) { return *p; }
 
 // ---- host versions of the PTX-level helpers of csrc/common.cuh -------------------------------------
 #define MADRL_EMU_PTX_HELPERS 1

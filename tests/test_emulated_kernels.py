@@ -729,3 +729,45 @@ def test_pipelined_host_rollout_chunks_and_obs_last_mode():
             assert f(c._h, T, _p(np.ascontiguousarray(act)), *[_p(x.arr) for x in bufs], 1, 2) == -1   # unknown flag
         finally:
             b.lib.madrl_set_host_chunk_bytes(0)
+
+
+@pytest.mark.parametrize("family", ["waterworld", "pursuit", "hostage"])
+def test_terminal_observations_are_kept_on_the_side(family):
+    """madrl_*_set_terminal_obs: with auto-reset the obs slot of a done step holds the reset observation;
+    the side tensor receives the observation the env returned before it was reset (what
+    StandardizedEnv.step sees first, madrl_environments/__init__.py:283-291); other slots stay untouched."""
+    import ctypes as C
+    from emu.driver import EmuHostage, EmuPursuit, EmuWaterworld, Guarded, _p
+    mpl, T, E = 5, 17, 3
+    if family == "waterworld":
+        mk = lambda **kw: EmuWaterworld(E, seed=6, fp64=True, **WW["c2"], **kw)          # noqa: E731
+        act = np.random.RandomState(0).randn(T, E, 5, 2)
+    elif family == "pursuit":
+        mk = lambda **kw: EmuPursuit(E, pool16(), seed=6, **C3, **kw)                     # noqa: E731
+        act = np.random.RandomState(0).randint(0, 5, size=(T, E, 8)).astype(np.int32)
+    else:
+        mk = lambda **kw: EmuHostage(E, 10, 16, 16, 4, 2, seed=6, fp64=True, **kw)        # noqa: E731
+        act = np.random.RandomState(0).randn(T, E, 10, 2)
+    a, b = mk(max_path_length=mpl), mk(max_path_length=mpl)
+    a.reset(), b.reset()
+    obs_a, rew_a, done_a, _ = a.rollout(act, auto_reset=True)
+    term = Guarded(obs_a.shape, obs_a.dtype, -7.0)
+    f = getattr(b.lib, "madrl_%s_set_terminal_obs" % b.fam)
+    f.argtypes = [C.c_void_p, C.c_void_p]
+    assert f(b._h, _p(term.arr)) == 0
+    obs_b, rew_b, done_b, _ = b.rollout(act, auto_reset=True)
+    assert f(b._h, None) == 0
+    t_arr = term.check("terminal obs")
+    assert np.array_equal(obs_a, obs_b) and np.array_equal(done_a, done_b) and done_a.sum() >= E * (T // mpl)
+    # reference run without auto-reset, reset by hand: its step obs at a done step is the terminal observation
+    c = mk(max_path_length=mpl)
+    c.reset()
+    for t in range(T):
+        o, _, d, _ = c.rollout(act[t:t + 1], auto_reset=False)
+        for e in range(E):
+            if d[0, e]:
+                assert np.array_equal(t_arr[t, e], o[0, e]), (t, e)
+            else:
+                assert (t_arr[t, e] == -7.0).all(), (t, e)
+        if d[0].any():
+            c.reset(mask=d[0])

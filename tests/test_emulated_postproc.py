@@ -182,3 +182,28 @@ def test_path_packing_kernels_equal_host_to_paths(lib):
                 for k in ('observations', 'actions', 'rewards'):
                     assert np.array_equal(g[k], w[k]), k
                 assert np.array_equal(g['env_infos']['k'], w['env_infos']['k'])
+
+
+def test_standardizer_with_terminal_observations_follows_the_reference_order(lib):
+    """madrl_standardize_obs_terminal_f32 vs the StandardizedEnv oracle (pinned to the real wrapper in
+    tests/test_postproc.py): at a done step the estimate sees the terminal observation first, then the
+    reset observation (step() then reset(), madrl_environments/__init__.py:283-291)."""
+    lib.madrl_standardize_obs_terminal_f32.argtypes = [C.c_int, C.c_int, C.c_size_t] + [C.c_void_p] * 5 + \
+        [C.c_double, C.c_double, C.c_void_p]
+    d = _data()
+    T, E, A, D = d['T'], d['E'], d['A'], d['D']
+    rs = np.random.RandomState(8)
+    term = rs.randn(T, E, A, D).astype(np.float32)
+    x, tm = d['obs'].copy(), term.copy()
+    mean, var = np.zeros((E, A, D)), np.ones((E, A, D))
+    assert lib.madrl_standardize_obs_terminal_f32(T, E, A * D, _p(x), _p(tm), _p(d['done']), _p(mean), _p(var),
+                                                  0.05, 1e-8, None) == 0
+    for e in range(E):
+        mine = po.StandardizeEnv(A, D, 1.0, True, False, 0.05, 0.001)
+        for t in range(T):
+            if d['done'][t, e]:
+                assert np.abs(np.array(mine.obs(term[t, e].astype(np.float64))) - tm[t, e]).max() < 1e-5, (t, e)
+            else:
+                assert np.array_equal(tm[t, e], term[t, e])          # untouched
+            assert np.abs(np.array(mine.obs(d['obs'][t, e].astype(np.float64))) - x[t, e]).max() < 1e-5, (t, e)
+        assert np.abs(np.array(mine.obs_mean) - mean[e]).max() < 1e-12

@@ -274,3 +274,40 @@ def test_cuda_pack_paths_matches_host_to_paths():
     pp2 = pack_paths(obs, act, rew, torch.zeros_like(done), None)
     assert len(pp2) == E * 5 and int(pp2.length.min()) == T
     assert torch.equal(pp2.path(6)['observations'], obs[:, 1, 1])
+
+
+@pytest.mark.gpu
+def test_cuda_terminal_obs_side_tensor_and_standardizer_order():
+    """engine.set_terminal_obs + Standardizer.obs(obs, done, terminal_obs) on the GPU: the side tensor
+    holds the pre-reset observation of every done step, and the running estimate follows the reference
+    order (terminal observation, then reset observation; madrl_environments/__init__.py:283-291)."""
+    import torch
+    from madrl_b200 import BatchedMAWaterWorld
+    from madrl_b200.postproc import Standardizer
+    E, T, mpl = 9, 23, 6
+    mk = lambda: BatchedMAWaterWorld(E, 5, 5, seed=5, max_path_length=mpl)          # noqa: E731
+    a, c = mk(), mk()
+    a.reset(), c.reset()
+    act = torch.randn(T, E, 5, 2, device="cuda") * 0.5
+    term = torch.full((T, E, 5, a.obs_dim), -7.0, device="cuda")
+    a.set_terminal_obs(term)
+    obs, rew, done, _ = a.rollout(act, auto_reset=True)
+    a.set_terminal_obs(None)
+    assert int(done.sum()) == E * (T // mpl)
+    for t in range(T):                                   # the same envs stepped without auto-reset
+        o, _, d, _ = c.rollout(act[t:t + 1], auto_reset=False)
+        hit = d[0].bool()
+        assert torch.equal(term[t][hit], o[0][hit]) and bool((term[t][~hit] == -7.0).all())
+        if hit.any():
+            c.reset(mask=d[0])
+    std = Standardizer(E, 5, a.obs_dim, "cuda", enable_obsnorm=True, obs_alpha=0.05)
+    x, tm = obs.clone(), term.clone()
+    std.obs(x, done, tm)
+    obs_h, term_h, done_h = obs.cpu().numpy(), term.cpu().numpy(), done.cpu().numpy()
+    for e in (0, 4, 8):
+        mine = StandardizeEnv(5, a.obs_dim, 1.0, True, False, 0.05, 0.001)
+        for t in range(T):
+            if done_h[t, e]:
+                assert np.abs(mine.obs(term_h[t, e].astype(np.float64)) - tm[t, e].cpu().numpy()).max() < 1e-4
+            assert np.abs(mine.obs(obs_h[t, e].astype(np.float64)) - x[t, e].cpu().numpy()).max() < 1e-4, (t, e)
+        assert np.abs(mine.obs_mean - std.obs_mean[e].cpu().numpy()).max() < 1e-9
