@@ -147,6 +147,18 @@ int madrl_ww_reset(madrl_ww* h, const uint8_t* mask_dev, void* obs_dev, void* st
  * slot of that step holds the reset observation. */
 int madrl_ww_rollout(madrl_ww* h, int T, const void* actions_dev, void* obs_dev, void* rew_dev,
                      uint8_t* done_dev, int32_t* info_dev, int auto_reset, void* stream);
+/* Closed-loop rollout: the actions come from the reference's hand-written policy
+ * (heuristics/waterworld.py:11-53 WaterworldHeuristicPolicy.sample_actions: flee the obstacle and poison,
+ * chase evaders, close in on allies; unit vector or zero), evaluated INSIDE the rollout kernel on the
+ * features each warp has just computed -- no action tensor is read, no per-step launch.
+ * obs0_dev real [E][Np][obs_dim]: the observation the first action is computed from (the reset
+ * observation, or the last observation of the previous rollout); actions_out_dev real [T][E][Np][2]
+ * receives the actions taken (NULL = not recorded).  Needs speed_features (the 7K layout the policy
+ * indexes).  Each agent row is normalised by its own norm (the reference is called per agent, B = 1).
+ * Other arguments as madrl_ww_rollout. */
+int madrl_ww_rollout_heuristic(madrl_ww* h, int T, const void* obs0_dev, void* actions_out_dev,
+                               void* obs_dev, void* rew_dev, uint8_t* done_dev, int32_t* info_dev,
+                               int auto_reset, void* stream);
 /* step() == rollout with T = 1. */
 int madrl_ww_step(madrl_ww* h, const void* actions_dev, void* obs_dev, void* rew_dev,
                   uint8_t* done_dev, int32_t* info_dev, int auto_reset, void* stream);
@@ -224,6 +236,20 @@ int madrl_pursuit_reset(madrl_pursuit* h, const uint8_t* mask_dev, float* obs_de
 int madrl_pursuit_rollout(madrl_pursuit* h, int T, const int32_t* actions_dev, float* obs_dev,
                           float* rew_dev, uint8_t* done_dev, int32_t* info_dev, int auto_reset,
                           void* stream);
+/* Closed-loop rollout: the pursuers' actions come from the reference's hand-written policy
+ * (heuristics/pursuit.py:18-50 PursuitHeuristicPolicy.sample_actions: walk towards the nearest evader of the
+ * observation window, a random move when none is visible), evaluated INSIDE the rollout kernel on the window
+ * each warp has just assembled.  obs0_dev float [E][Np][obs_dim]: the observation the first action is
+ * computed from; actions_out_dev int32 [T][E][Np] receives the actions taken (NULL = not recorded).
+ * floor_centre != 0: the window centre is (R//2, R//2) -- what `xs / 2` (heuristics/pursuit.py:23) gives under
+ * Python 2, the reference's language; 0: (R/2, R/2) true division, what the same line gives under Python 3.
+ * The policy's own draws (`action_space.sample()`, :48,50) are an injected counter-based stream: pursuer q
+ * deciding on an observation produced when the env's draw counter stood at c takes word 32 c + q of the
+ * (seed, env id, tag 2) Philox stream, mapped to {0..4} like every other range draw.  Other arguments as
+ * madrl_pursuit_rollout. */
+int madrl_pursuit_rollout_heuristic(madrl_pursuit* h, int T, const float* obs0_dev, int32_t* actions_out_dev,
+                                    float* obs_dev, float* rew_dev, uint8_t* done_dev, int32_t* info_dev,
+                                    int auto_reset, int floor_centre, void* stream);
 int madrl_pursuit_step(madrl_pursuit* h, const int32_t* actions_dev, float* obs_dev, float* rew_dev,
                        uint8_t* done_dev, int32_t* info_dev, int auto_reset, void* stream);
 int madrl_pursuit_reset_host(madrl_pursuit* h, const uint8_t* mask_host, float* obs_host);
@@ -289,6 +315,24 @@ int madrl_hostage_rollout_host(madrl_hostage* h, int T, const void* actions_host
 int madrl_hostage_rollout_host2(madrl_hostage* h, int T, const void* actions_host, void* obs_host,
                                 void* rew_host, uint8_t* done_host, int32_t* info_host,
                                 int auto_reset, int flags);
+
+/* ------------------------------------------------------------------ hand-written policies -----
+ * The reference's heuristic policies as stand-alone action generators over n_rows observation rows (one
+ * row = one agent's observation), for callers that step an env one batch at a time; the
+ * `*_rollout_heuristic` entry points above evaluate the same policies inside the rollout kernels.
+ * madrl_ww_heuristic_actions       heuristics/waterworld.py:11-53: obs real [n_rows][obs_dim] in the 7K+2(+1)
+ *                                  layout (:12-22) -> actions real [n_rows][2]; each row normalised by its own
+ *                                  norm (the reference is called per agent).
+ * madrl_pursuit_heuristic_actions  heuristics/pursuit.py:18-50: obs float [n_rows][obs_dim], flatten != 0: the
+ *                                  (3R^2 [+1]) layout, else (R, R, 4); fallback int32 [n_rows] = the action taken
+ *                                  when no evader is visible (`action_space.sample()`, drawn by the caller);
+ *                                  floor_centre as in madrl_pursuit_rollout_heuristic; lut_dev: R*R bytes of
+ *                                  device scratch (the per-cell action table, filled by the call). */
+int madrl_ww_heuristic_actions(int fp64, size_t n_rows, int n_sensors, int obs_dim, const void* obs_dev,
+                               void* actions_dev, void* stream);
+int madrl_pursuit_heuristic_actions(size_t n_rows, int obs_range, int flatten, int obs_dim, int floor_centre,
+                                    const float* obs_dev, const int32_t* fallback_dev, uint8_t* lut_dev,
+                                    int32_t* actions_dev, void* stream);
 
 /* ------------------------------------------------------------------ trajectory post-processing
  * (SURVEY.md 8f rows 2-3).  All tensors are device pointers, float32 unless noted, time-major. */

@@ -20,6 +20,7 @@
 //   * Observation rows are written cell-major: lane w handles window cell w for all 3 channels
 //     (shared coordinate math), three coalesced stores per 32 cells.
 #include <math.h>
+#include <string.h>
 #include <new>
 
 #include "common.cuh"
@@ -55,7 +56,17 @@ struct PEParams {
   int32_t* info;                  // [T][E]  removed
   const uint8_t* mask;
   float* term_obs;                // optional [T][E][Np][D]: terminal observations of done steps
+  // in-kernel action source (POLICY instantiation, madrl_pursuit_rollout_heuristic): the reference's
+  // hand-written policy (heuristics/pursuit.py:18-50) closes the loop inside the launch
+  const float* policy_obs0;       // [E][Np][D] the observation the FIRST action is computed from
+  int32_t* actions_out;           // [T][E][Np] the actions taken (NULL = not recorded)
+  int policy_c2;                  // twice the policy's window centre: R (x = R/2) or 2*(R//2) (Python 2 `/`)
+  uint8_t policy_lut[128];        // window cell of the nearest visible evader -> action (host-computed, see pe_policy_table)
 };
+
+// Stream family of the policy's own draws (heuristics/pursuit.py:48,50 `action_space.sample()`): pursuer q
+// deciding on an observation that was produced when the env's draw counter stood at c takes word 32 c + q.
+constexpr uint32_t PE_POLICY_TAG = 2u;
 
 // float64 `ndarray.mean()` exactly as NumPy (>= 1.22, checked against 2.3.5) computes it for a
 // contiguous vector of n <= 128 elements: DOUBLE_pairwise_sum over the WHOLE vector
@@ -81,7 +92,9 @@ __device__ __forceinline__ double numpy_mean(const double* a, int n) {
 
 // EPL = evaders per lane (ceil(Ne/32)); CPL = window cells per lane (ceil(R*R/32));
 // RC = compile-time obs_range (0 = runtime p.R).
-template <int EPL, int CPL, int RC>
+// POLICY = the pursuers' actions come from the in-kernel heuristic policy instead of the action tensor
+// (a separate instantiation: the open-loop kernel carries none of its instructions).
+template <int EPL, int CPL, int RC, bool POLICY = false>
 __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEParams p) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   const int lane = threadIdx.x, wib = 0;
@@ -108,6 +121,16 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
     wdy[it] = w % R - p.off;
   }
   const int n_tail = p.include_id ? 1 : 0;
+  // POLICY: sort key of window cell w as "nearest visible evader" (heuristics/pursuit.py:28-31): squared
+  // distance to the window centre in doubled coordinates (sqrt is monotonic and these small integers have
+  // distinct roots), then the row-major cell index -- np.nonzero order, np.argmin keeps the first minimum
+  uint32_t pkey[CPL];
+#pragma unroll
+  for (int it = 0; it < CPL; ++it) {
+    const int w = lane + 32 * it;
+    const int ddx = 2 * (w / R) - p.policy_c2, ddy = 2 * (w % R) - p.policy_c2;
+    pkey[it] = ((uint32_t)(ddx * ddx + ddy * ddy) << 8) | (uint32_t)w;
+  }
 
   for (int e = warp_global; e < p.E; e += warp_stride) {
     if (p.mode == 1 && p.mask != nullptr && p.mask[e] == 0) continue;
@@ -138,9 +161,31 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
     const int32_t* act_t = p.actions + (size_t)e * Np + lane;
     size_t te = (size_t)e;
     int pass = (p.mode == 1) ? 1 : 0;   // pass 1 = reset(): draws + obs only
+    // POLICY: pursuer `lane`'s action for the NEXT step, first from the caller's observation
+    int next_act = 4;
+    if constexpr (POLICY) {
+      const float* o0 = p.policy_obs0 + (size_t)e * Np * p.D;
+      for (int i = 0; i < Np; ++i, o0 += p.D) {
+        uint32_t key = 0xffffffffu;
+#pragma unroll
+        for (int it = 0; it < CPL; ++it) {
+          const int w = lane + 32 * it;
+          if (w < RR && (p.flatten ? o0[2 * RR + w] : o0[4 * w + 2]) > 0.0f) key = min(key, pkey[it]);
+        }
+        key = __reduce_min_sync(FULL_MASK, key);
+        if (lane == i)
+          next_act = key != 0xffffffffu ? (int)p.policy_lut[key & 0xffu]
+                                        : u32_to_range(stream_word(p.seed, env_id, PE_POLICY_TAG, ctr * 32u + (uint64_t)i), 0, 5);
+      }
+    }
     for (int t = 0; t < p.T; ++t) {
       int act = 4;
-      if (p.mode == 0 && lane < Np) {
+      if constexpr (POLICY) {
+        if (lane < Np) {
+          act = next_act;
+          if (p.actions_out != nullptr) p.actions_out[(size_t)t * p.agent_step + (size_t)e * Np + lane] = act;
+        }
+      } else if (p.mode == 0 && lane < Np) {
         act = *act_t;
         if (t + 1 < p.T) prefetch_l1(act_t + p.agent_step);   // next step's action -> L1
       }
@@ -326,6 +371,16 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
               if (w < RR) sts_u16(st_row + 2u * w, c12[it]);
               v1[it] = lds_f32(lut_a + 4u * (c12[it] & 0xffu));         // float32(k) / float32(layer_norm)
               v2[it] = lds_f32(lut_a + 4u * (c12[it] >> 8));
+            }
+            if constexpr (POLICY) {   // heuristics/pursuit.py:18-50 on the evader channel just assembled
+              uint32_t key = 0xffffffffu;
+#pragma unroll
+              for (int it = 0; it < CPL; ++it)
+                if (lane + 32 * it < RR && (c12[it] >> 8) != 0u) key = min(key, pkey[it]);
+              key = __reduce_min_sync(FULL_MASK, key);
+              if (lane == i)
+                next_act = key != 0xffffffffu ? (int)p.policy_lut[key & 0xffu]
+                                              : u32_to_range(stream_word(p.seed, env_id, PE_POLICY_TAG, ctr * 32u + (uint64_t)i), 0, 5);
             }
             if (p.flatten) {
 #pragma unroll
@@ -554,10 +609,34 @@ extern "C" int madrl_pursuit_set_params(madrl_pursuit* h, double catchr, double 
   return MADRL_OK;
 }
 
-template <int EPL, int CPL, int RC>
-static int pe_launch_inst(madrl_pursuit* h, PEParams& p, cudaStream_t stream) {
+// heuristics/pursuit.py:23-48 for every window cell the nearest visible evader can occupy: the action a
+// pursuer at the window centre (x, y) = (c2/2, c2/2) takes towards cell (xc, yc).  Same double arithmetic as
+// the reference (libm atan2, Python's float `%`), evaluated once on the host.
+void pe_policy_table(int R, int c2, uint8_t* lut) {
+  const double pi = 3.141592653589793;   // np.pi
+  const double x = 0.5 * (double)c2, y = 0.5 * (double)c2;
+  for (int w = 0; w < R * R && w < 128; ++w) {
+    const double xc = (double)(w / R), yc = (double)(w % R);
+    int a;
+    if (xc == x && yc == y) a = 4;                                     // STAY  :33-34
+    else {
+      double ang = atan2(yc - y, xc - x);                              // :35
+      double m = fmod(ang + pi, 2 * pi);                               // :36  Python `%`: sign of the divisor
+      if (m < 0) m += 2 * pi;
+      ang = m - pi;
+      if (-pi / 4 <= ang && ang < pi / 4) a = 1;                       // RIGHT :38
+      else if (pi / 4 <= ang && ang < 3 / 4. * pi) a = 2;              // UP    :41
+      else if (ang >= 3 / 4. * pi || ang < -3 / 4. * pi) a = 0;        // LEFT  :44
+      else a = 3;                                                      // DOWN  :47 (the final `else` is unreachable)
+    }
+    lut[w] = (uint8_t)a;
+  }
+}
+
+template <int EPL, int CPL, int RC, bool POLICY>
+static int pe_launch_inst2(madrl_pursuit* h, PEParams& p, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)p.smem_per_warp;   // block LUT + per-warp regions
-  const auto kfn = pe_kernel<EPL, CPL, RC>;
+  const auto kfn = pe_kernel<EPL, CPL, RC, POLICY>;
   MADRL_REQUIRE(smem <= 200 * 1024, "map too large for shared memory (%zu B per block)", smem);
   if (smem > 48 * 1024)
     MADRL_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -573,10 +652,20 @@ static int pe_launch_inst(madrl_pursuit* h, PEParams& p, cudaStream_t stream) {
   return MADRL_OK;
 }
 
+template <int EPL, int CPL, int RC>
+static int pe_launch_inst(madrl_pursuit* h, PEParams& p, cudaStream_t stream) {
+  return p.policy_obs0 != nullptr ? pe_launch_inst2<EPL, CPL, RC, true>(h, p, stream)
+                                  : pe_launch_inst2<EPL, CPL, RC, false>(h, p, stream);
+}
+
 static int pe_launch(madrl_pursuit* h, int mode, int T, const int32_t* actions, float* obs, float* rew,
-                     uint8_t* done, int32_t* info, const uint8_t* mask, int auto_reset, cudaStream_t stream) {
+                     uint8_t* done, int32_t* info, const uint8_t* mask, int auto_reset, cudaStream_t stream,
+                     const float* policy_obs0 = nullptr, int32_t* actions_out = nullptr, int policy_c2 = 0) {
   const madrl_pursuit_config& c = h->cfg;
   PEParams p;
+  p.policy_obs0 = policy_obs0; p.actions_out = actions_out; p.policy_c2 = policy_c2;
+  memset(p.policy_lut, 4, sizeof(p.policy_lut));
+  if (policy_obs0 != nullptr) pe_policy_table(c.obs_range, policy_c2, p.policy_lut);
   p.E = c.n_envs; p.env_id_base = c.env_id_base; p.Np = c.n_pursuers; p.Ne = c.n_evaders;
   p.R = c.obs_range; p.off = (int)((c.obs_range - 1) / 2);   // pe:65
   p.xs = c.xs; p.ys = c.ys; p.n_maps = c.n_maps; p.D = h->lay.obs_dim;
@@ -625,6 +714,18 @@ extern "C" int madrl_pursuit_rollout(madrl_pursuit* h, int T, const int32_t* act
   MADRL_REQUIRE(T >= 1, "T must be >= 1");
   MADRL_REQUIRE(actions_dev && obs_dev && rew_dev && done_dev && info_dev, "NULL trajectory buffer");
   return pe_launch(h, 0, T, actions_dev, obs_dev, rew_dev, done_dev, info_dev, nullptr, auto_reset, (cudaStream_t)stream);
+}
+
+extern "C" int madrl_pursuit_rollout_heuristic(madrl_pursuit* h, int T, const float* obs0_dev, int32_t* actions_out_dev,
+                                               float* obs_dev, float* rew_dev, uint8_t* done_dev, int32_t* info_dev,
+                                               int auto_reset, int floor_centre, void* stream) {
+  MADRL_REQUIRE(h != nullptr, "handle is NULL");
+  MADRL_REQUIRE(T >= 1, "T must be >= 1");
+  MADRL_REQUIRE(obs0_dev && obs_dev && rew_dev && done_dev && info_dev, "NULL trajectory buffer");
+  MADRL_REQUIRE(h->cfg.layer_norm > 0.0, "the heuristic policy tests `evader channel > 0`: layer_norm must be positive");
+  const int R = h->cfg.obs_range;
+  return pe_launch(h, 0, T, nullptr, obs_dev, rew_dev, done_dev, info_dev, nullptr, auto_reset, (cudaStream_t)stream,
+                   obs0_dev, actions_out_dev, floor_centre ? 2 * (R / 2) : R);
 }
 
 extern "C" int madrl_pursuit_step(madrl_pursuit* h, const int32_t* actions_dev, float* obs_dev, float* rew_dev,

@@ -59,6 +59,10 @@ struct WWParams {
   int32_t* info;
   const uint8_t* mask;
   real* term_obs;   // optional [T][E][A][D]: terminal observations of done steps (see keep_terminal_rows)
+  // in-kernel action source (POLICY instantiation, madrl_ww_rollout_heuristic): the reference's hand-written
+  // policy (heuristics/waterworld.py:11-53) closes the loop inside the launch -- no action tensor is read
+  const real* policy_obs0;   // [E][Np][D] the observation the FIRST action is computed from
+  real* actions_out;         // [T][E][Np][2] the actions taken (NULL = not recorded)
   // fused per-rollout exchange (multi-GPU): every rank also stores its reward / done / info rows
   // into slot `peer_rank` of each destination gather buffer through NVLink peer mappings (CUDA
   // IPC).  Rows are staged in registers and written as coalesced runs (rewards every 32/Np steps,
@@ -80,6 +84,13 @@ __device__ __forceinline__ real warp_sum(real v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
   return v;
 }
+
+// 0 <= sv < best for best > 0, in one comparison for float: non-negative floats order like their bit patterns
+// and every negative one has the sign bit set, i.e. compares above any positive `best` as an unsigned integer.
+// (-0.0 would be rejected where `sv < 0` is false, but sx * jx + sy * jy in round-to-nearest only yields -0.0
+// from two negative-zero terms, and neither a position difference nor a product with one can be -0.0 here.)
+__device__ __forceinline__ bool in_zero_to(float sv, float best) { return __float_as_uint(sv) < __float_as_uint(best); }
+__device__ __forceinline__ bool in_zero_to(double sv, double best) { return !(sv < 0.0) && sv < best; }
 
 template <typename real>
 struct Spawn { real x, y, vx, vy; uint64_t ctr; };
@@ -116,7 +127,9 @@ __device__ __noinline__ Spawn<real> spawn_object(uint64_t seed, uint32_t env_id,
 // pursuer use immediate offsets from one running pointer instead of 64-bit address arithmetic.
 // PEER = compile the fused multi-GPU exchange in (a separate instantiation, so the single-GPU kernel
 // carries none of its registers).
-template <typename real, int OPL, int KCH, int KC, bool PEER>
+// POLICY = the actions come from the in-kernel heuristic policy instead of the action tensor (again a
+// separate instantiation: the open-loop kernel carries none of its instructions).
+template <typename real, int OPL, int KCH, int KC, bool PEER, bool POLICY = false>
 __global__ void __launch_bounds__(32, (OPL <= 4 ? 28 : 16))
 ww_kernel(const __grid_constant__ WWParams<real> p) {
   const real INF = real_inf<real>();
@@ -129,9 +142,11 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
   const int warp_stride = gridDim.x;
   const int eLo = p.Np, eHi = p.Np + p.Ne, Nall = p.Nall;
   constexpr bool SMEM = OPL >= 2;
+  const unsigned lt_mask = lanemask_lt();
   extern __shared__ __align__(16) unsigned char ww_smem[];
   // this warp's candidate slots (32-bit shared address)
-  const uint32_t slots = SMEM ? smem_addr(ww_smem) : 0u;
+  uint32_t slots = SMEM ? smem_addr(ww_smem) : 0u;
+  asm volatile("" : "+r"(slots));   // keep it in a register: ptxas otherwise re-derives it from SR_CgaCtaId at every use
 
   // ---- per-lane constants: this lane as OBJECT (classes, thresholds) and as SENSOR -----------
   real cull2_l[OPL], coll2_l[OPL];
@@ -140,7 +155,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
   for (int c = 0; c < OPL; ++c) {
     const int o = lane + 32 * c;
     const bool isU = o < eLo, isE = o >= eLo && o < eHi, isP = o >= eHi && o < Nall;
-    cull2_l[c] = (o < Nall) ? p.cull2 : (real)-1;
+    cull2_l[c] = p.cull2;   // uniform: lanes beyond the last object hold a far-away sentinel position instead
     coll2_l[c] = isE ? p.coll2_e : (isP ? p.coll2_po : (real)-1);
     mU[c] = __ballot_sync(FULL_MASK, isU);
     mE[c] = __ballot_sync(FULL_MASK, isE);
@@ -167,8 +182,8 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     for (int c = 0; c < OPL; ++c) {
       const int o = lane + 32 * c;
       const bool v = o < Nall;
-      x[c] = v ? rec[o] : (real)0;
-      y[c] = v ? rec[Nall + o] : (real)0;
+      x[c] = v ? rec[o] : (real)1e18;            // sentinel: never in range of anything, never written back
+      y[c] = v ? rec[Nall + o] : (real)1e18;
       vx[c] = v ? rec[2 * Nall + o] : (real)0;
       vy[c] = v ? rec[3 * Nall + o] : (real)0;
       col[c] = 0u;
@@ -184,6 +199,28 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     int pass = (p.mode == 1) ? 1 : 0;  // pass 1 = reset pass: fresh draws, zero action, obs only
     const V2* act_t = reinterpret_cast<const V2*>(p.actions) + (size_t)e * p.Np + lane;
 
+    // POLICY: un-normalised action of pursuer `lane` for the NEXT step (heuristics/waterworld.py:25-44),
+    // first from the caller's observation, afterwards from the features this warp has just computed
+    real pax = 0, pay = 0;
+    if constexpr (POLICY) {
+      const real* o0 = p.policy_obs0 + (size_t)e * p.Np * p.D;
+      for (int pi = 0; pi < p.Np; ++pi, o0 += p.D) {
+        const real cE = o0[7 * K] > (real)0 ? (real)1.5 : (real)1;        // heuristics/waterworld.py:41
+        const real cP = o0[7 * K + 1] > (real)0 ? (real)1.5 : (real)1;    // :42
+        real wx = 0, wy = 0;
+#pragma unroll
+        for (int kc = 0; kc < KCH; ++kc) {
+          const int k = lane + 32 * kc;
+          if (k < K) {
+            const real w = (real)0.5 * o0[5 * K + k] + (cE * o0[K + k] - o0[k]) - cP * o0[3 * K + k];
+            wx += w * sx_l[kc]; wy += w * sy_l[kc];
+          }
+        }
+        wx = warp_sum(wx); wy = warp_sum(wy);
+        if (lane == pi) { pax = wx; pay = wy; }
+      }
+    }
+
     // staging registers of the fused exchange
     const int rew_per = 32 / p.Np;                       // steps per coalesced reward run
     const int stage_src = lane % p.Np, stage_step = lane / p.Np;
@@ -196,7 +233,19 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     for (int t = 0; t < p.T; ++t) {
       V2 act;
       act.x = 0; act.y = 0;
-      if (p.mode == 0 && lane < p.Np) {
+      if constexpr (POLICY) {
+        if (lane < p.Np) {   // heuristics/waterworld.py:44-50: unit vector, or zero when nothing is sensed
+          // scaled by the larger component first: the squares of a tiny sum (cancellation leaves ~1e-21) would be
+          // denormal in float32 and the "unit" vector off by 1e-4
+          const real m = fmax(fabs(pax), fabs(pay));
+          if (m > (real)0) {
+            const real ux = pax / m, uy = pay / m, n = sqrt(ux * ux + uy * uy);
+            act.x = ux / n; act.y = uy / n;
+          }
+          if (p.actions_out != nullptr)
+            reinterpret_cast<V2*>(p.actions_out)[(size_t)t * p.agent_step + (size_t)e * p.Np + lane] = act;
+        }
+      } else if (p.mode == 0 && lane < p.Np) {
         act = *act_t;
         if (t + 1 < p.T) prefetch_l1(act_t + p.agent_step);   // next step's action -> L1
       }
@@ -262,6 +311,8 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
           int iE[KCH], iP[KCH], iU[KCH];
           const real orx = obx - mx, ory = oby - my;
           const real od2 = orx * orx + ory * ory;
+          real pwx = 0, pwy = 0;       // POLICY: this lane's share of pursuer pi's next action
+          unsigned tE = 0u, tP = 0u;   // POLICY: evaders / poisons pursuer pi touches this step (obs[7K], obs[7K+1])
 #pragma unroll
           for (int kc = 0; kc < KCH; ++kc) {
             bO[kc] = bE[kc] = bP[kc] = bU[kc] = INF;
@@ -274,7 +325,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
           }
           if constexpr (SMEM) {
             constexpr uint32_t S = CandSlot<real>::kStride;
-            uint32_t endU = slots, nEc = 0u, nPc = 0u, top = slots;
+            uint32_t endU = slots, nEc = 0u, top = slots;
 #pragma unroll
             for (int c = 0; c < OPL; ++c) {
               // lanes as OBJECTS: geometry, collisions (ww:278-293), conservative range cull, staging
@@ -284,16 +335,16 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
               const unsigned cm = __ballot_sync(FULL_MASK, near);
               const bool hit = d2 <= coll2_l[c];
               if (hit) col[c] |= 1u << pi;
+              if constexpr (POLICY) { const unsigned hm = __ballot_sync(FULL_MASK, hit); tE |= hm & mE[c]; tP |= hm & mP[c]; }
               // slot = rank among the candidates in ascending object index (= lane + 32 c)
-              if (near) CandSlot<real>::put(top + (uint32_t)__popc(cm & ((1u << lane) - 1u)) * S, rx, ry, d2, vx[c], vy[c]);
+              if (near) CandSlot<real>::put(top + (uint32_t)__popc(cm & lt_mask) * S, rx, ry, d2, vx[c], vy[c]);
               if (c == 0) endU = slots + (uint32_t)__popc(cm & mU[0]) * S;   // pursuers live in chunk 0 (Np <= 32)
               nEc += (uint32_t)__popc(cm & mE[c]);
-              nPc += (uint32_t)__popc(cm & mP[c]);
               top += (uint32_t)__popc(cm) * S;
             }
             __syncwarp();
             // lanes as SENSORS: classes are contiguous in object index, hence in slot order U, E, P
-            const uint32_t endE = endU + nEc * S, endP = endE + nPc * S;
+            const uint32_t endE = endU + nEc * S, endP = top;   // the poisons end the list
             const real up = p.range_up;   // `sv < up` <=> `sv <= range`; a best below `up` <=> sensed
             uint32_t aE[KCH], aP[KCH], aU[KCH];
 #pragma unroll
@@ -305,8 +356,8 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     CandSlot<real>::geom(a, jx, jy, jd);                                                 \
     _Pragma("unroll") for (int kc = 0; kc < KCH; ++kc) {                                 \
       const real sv = sx_l[kc] * jx + sy_l[kc] * jy;                                     \
-      const bool ok = !((sv < (real)0) | (jd - sv * sv > p.r_p2));                       \
-      if (ok && sv < BEST[kc]) { BEST[kc] = sv; AT[kc] = a; }                            \
+      /* ww:64-72: 0 <= sv (<= range, through the initial best) and within the pursuer's radius of the ray */ \
+      if (in_zero_to(sv, BEST[kc]) && !(jd - sv * sv > p.r_p2)) { BEST[kc] = sv; AT[kc] = a; } \
     }                                                                                    \
   }
             MADRL_WW_SCAN(slots, endU, bU, aU)
@@ -321,6 +372,13 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
               const bool hO = bO[kc] < INF, hE = bE[kc] < up, hP = bP[kc] < up, hU = bU[kc] < up;
               const real z = (real)0;
               real* o = obs_row + 32 * kc;   // this lane's column
+              if constexpr (POLICY) {
+                if (k < K) {
+                  const real w = (real)0.5 * (hU ? bU[kc] : z) + ((tE ? (real)1.5 : (real)1) * (hE ? bE[kc] : z) - (hO ? bO[kc] : z)) -
+                                 (tP ? (real)1.5 : (real)1) * (hP ? bP[kc] : z);
+                  pwx += w * sx; pwy += w * sy;
+                }
+              }
               if (p.speed_features) {
                 // slot 0 is read when nothing was sensed; its (possibly stale) value is masked below
                 real oEx, oEy, oPx, oPy, oUx, oUy;
@@ -354,6 +412,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
             if (c == 0) cm &= ~(1u << pi);  // ww:70-71 `same`
             const bool hit = d2 <= coll2_l[c];
             if (hit) col[c] |= 1u << pi;
+            if constexpr (POLICY) { const unsigned hm = __ballot_sync(FULL_MASK, hit); tE |= hm & mE[c]; tP |= hm & mP[c]; }
             // lanes as SENSORS: scan the surviving candidates of this chunk, ascending index
 #pragma unroll
             for (int kc = 0; kc < KCH; ++kc) {
@@ -381,6 +440,13 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
             const bool hO = bO[kc] < INF, hE = bE[kc] < INF, hP = bP[kc] < INF, hU = bU[kc] < INF;
             const real z = (real)0;
             real* o = obs_row + 32 * kc;   // this lane's column
+            if constexpr (POLICY) {
+              if (k < K) {
+                const real w = (real)0.5 * (hU ? bU[kc] : z) + ((tE ? (real)1.5 : (real)1) * (hE ? bE[kc] : z) - (hO ? bO[kc] : z)) -
+                               (tP ? (real)1.5 : (real)1) * (hP ? bP[kc] : z);
+                pwx += w * sx; pwy += w * sy;
+              }
+            }
             if (p.speed_features) {
               real oEx, oEy, oPx, oPy, oUx, oUy;
               if (OPL == 1) {
@@ -415,6 +481,10 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
               store_stream(o + 3 * K, hU ? bU[kc] : z);
             }
           }
+          }
+          if constexpr (POLICY) {   // sum over the sensors; lane pi keeps pursuer pi's next action
+            pwx = warp_sum(pwx); pwy = warp_sum(pwy);
+            if (lane == pi) { pax = pwx; pay = pwy; }
           }
         }
         // ---- catches, respawn, rewards: ww:285,293,358-385 -----------------------------------------
@@ -708,9 +778,9 @@ static real exact_sq_threshold(double thr_d) {
   return t;
 }
 
-template <typename real, int OPL, int KCH, int KC, bool PEER>
+template <typename real, int OPL, int KCH, int KC, bool PEER, bool POLICY>
 static int ww_launch_inst2(madrl_ww* h, const WWParams<real>& p, cudaStream_t stream) {
-  const auto kfn = ww_kernel<real, OPL, KCH, KC, PEER>;
+  const auto kfn = ww_kernel<real, OPL, KCH, KC, PEER, POLICY>;
   int resident = 0;
   const size_t smem = OPL >= 2 ? (size_t)p.Nall * CandSlot<real>::kStride : 0;   // candidate slots
   if (smem > 48 * 1024)
@@ -729,14 +799,15 @@ static int ww_launch_inst2(madrl_ww* h, const WWParams<real>& p, cudaStream_t st
 
 template <typename real, int OPL, int KCH, int KC>
 static int ww_launch_inst(madrl_ww* h, const WWParams<real>& p, cudaStream_t stream) {
-  return p.n_peers > 0 ? ww_launch_inst2<real, OPL, KCH, KC, true>(h, p, stream)
-                       : ww_launch_inst2<real, OPL, KCH, KC, false>(h, p, stream);
+  if (p.policy_obs0 != nullptr) return ww_launch_inst2<real, OPL, KCH, KC, false, true>(h, p, stream);
+  return p.n_peers > 0 ? ww_launch_inst2<real, OPL, KCH, KC, true, false>(h, p, stream)
+                       : ww_launch_inst2<real, OPL, KCH, KC, false, false>(h, p, stream);
 }
 
 template <typename real>
 static int ww_launch(madrl_ww* h, int mode, int T, const void* actions, void* obs, void* rew,
                      uint8_t* done, int32_t* info, const uint8_t* mask, int auto_reset,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const void* policy_obs0 = nullptr, void* actions_out = nullptr) {
   const madrl_ww_config& c = h->cfg;
   WWParams<real> p;
   p.E = c.n_envs; p.env_id_base = c.env_id_base;
@@ -777,7 +848,9 @@ static int ww_launch(madrl_ww* h, int mode, int T, const void* actions, void* ob
   p.actions = (const real*)actions; p.obs = (real*)obs; p.rew = (real*)rew;
   p.done = done; p.info = info; p.mask = mask;
   p.term_obs = (mode == 0) ? (real*)h->term_obs : nullptr;
-  p.n_peers = (mode == 0) ? h->n_peers : 0;
+  p.policy_obs0 = (const real*)policy_obs0; p.actions_out = (real*)actions_out;
+  // the policy instantiation is single-GPU: its rows go through the copy-engine exchange, not peer stores
+  p.n_peers = (mode == 0 && policy_obs0 == nullptr) ? h->n_peers : 0;
   p.peer_rank = h->peer_rank;
   if (p.n_peers > 0) {
     MADRL_REQUIRE(T <= h->peer_tmax, "rollout of %d steps exceeds the peer buffers (t_max %d)", T, h->peer_tmax);
@@ -825,6 +898,20 @@ extern "C" int madrl_ww_rollout(madrl_ww* h, int T, const void* actions_dev, voi
   MADRL_REQUIRE(((uintptr_t)info_dev & 7) == 0, "info_dev must be 8-byte aligned (rows are stored as one 8-byte word)");
   return h->cfg.fp64 ? ww_launch<double>(h, 0, T, actions_dev, obs_dev, rew_dev, done_dev, info_dev, nullptr, auto_reset, (cudaStream_t)stream)
                      : ww_launch<float>(h, 0, T, actions_dev, obs_dev, rew_dev, done_dev, info_dev, nullptr, auto_reset, (cudaStream_t)stream);
+}
+
+extern "C" int madrl_ww_rollout_heuristic(madrl_ww* h, int T, const void* obs0_dev, void* actions_out_dev,
+                                          void* obs_dev, void* rew_dev, uint8_t* done_dev, int32_t* info_dev,
+                                          int auto_reset, void* stream) {
+  MADRL_REQUIRE(h != nullptr, "handle is NULL");
+  MADRL_REQUIRE(T >= 1, "T must be >= 1");
+  MADRL_REQUIRE(obs0_dev && obs_dev && rew_dev && done_dev && info_dev, "NULL trajectory buffer");
+  MADRL_REQUIRE(((uintptr_t)info_dev & 7) == 0, "info_dev must be 8-byte aligned (rows are stored as one 8-byte word)");
+  MADRL_REQUIRE(((uintptr_t)actions_out_dev & (h->cfg.fp64 ? 15 : 7)) == 0, "actions_out_dev must be aligned to one (x, y) pair");
+  MADRL_REQUIRE(h->cfg.speed_features, "the heuristic policy reads the 7K feature layout (speed_features=True; "
+                                       "heuristics/waterworld.py:12-22)");
+  return h->cfg.fp64 ? ww_launch<double>(h, 0, T, nullptr, obs_dev, rew_dev, done_dev, info_dev, nullptr, auto_reset, (cudaStream_t)stream, obs0_dev, actions_out_dev)
+                     : ww_launch<float>(h, 0, T, nullptr, obs_dev, rew_dev, done_dev, info_dev, nullptr, auto_reset, (cudaStream_t)stream, obs0_dev, actions_out_dev);
 }
 
 extern "C" int madrl_ww_step(madrl_ww* h, const void* actions_dev, void* obs_dev, void* rew_dev,

@@ -175,6 +175,30 @@ class BatchedPursuitEvade(object):
                                                      _ptr(done), _ptr(info), int(auto_reset), self._stream()))
         return obs, rew, done, info
 
+    def rollout_heuristic(self, T, obs0, auto_reset=True, out=None, record_actions=True, py2_division=True):
+        """T lockstep steps in one launch with the reference's hand-written policy
+        (heuristics/pursuit.py:18-50: walk towards the nearest visible evader, a random move when none is
+        visible) evaluated inside the kernel: closed loop, no action tensor, no per-step launch.
+        obs0 [E, Np, D] = the observation the first action is computed from (`reset()`'s, or `obs[-1]` of
+        the previous rollout).  `py2_division`: the window centre `xs / 2` (heuristics/pursuit.py:23) as
+        Python 2 -- the reference's language -- computes it (R // 2); False = Python 3 true division.
+        Returns (actions int32 [T,E,Np] or None, obs, rew, done, removed)."""
+        E, Np, D = self.n_envs, self.n_pursuers, self.obs_dim
+        _lib.require_tensor(obs0, "obs0", torch.float32, (E, Np, D), self.device)
+        if out is None:
+            obs = torch.empty((T, E, Np, D), dtype=torch.float32, device=self.device)
+            rew = torch.empty((T, E, Np), dtype=torch.float32, device=self.device)
+            done = torch.empty((T, E), dtype=torch.uint8, device=self.device)
+            info = torch.empty((T, E), dtype=torch.int32, device=self.device)
+        else:
+            obs, rew, done, info = self._require_outputs(T, out, self.device)
+        act = torch.empty((T, E, Np), dtype=torch.int32, device=self.device) if record_actions else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.madrl_pursuit_rollout_heuristic(
+                self._h, T, _ptr(obs0), _ptr(act), _ptr(obs), _ptr(rew), _ptr(done), _ptr(info), int(auto_reset),
+                int(bool(py2_division)), self._stream()))
+        return act, obs, rew, done, info
+
     def step(self, actions, auto_reset=False):
         a = torch.as_tensor(actions, device=self.device).to(torch.int32).reshape(1, self.n_envs, self.n_pursuers)
         obs, rew, done, info = self.rollout(a, auto_reset=auto_reset)

@@ -196,6 +196,27 @@ class BatchedMAWaterWorld(object):
                                                 _ptr(done), _ptr(info), int(auto_reset), self._stream()))
         return obs, rew, done, info
 
+    def rollout_heuristic(self, T, obs0, auto_reset=True, out=None, record_actions=True):
+        """T lockstep steps in one launch with the reference's hand-written policy
+        (heuristics/waterworld.py:11-53) evaluated inside the kernel: closed loop, no action tensor,
+        no per-step launch.  obs0 [E, Np, D] = the observation the first action is computed from
+        (`reset()`'s, or `obs[-1]` of the previous rollout).  Returns
+        (actions [T,E,Np,2] or None, obs, rew, done, info)."""
+        E, Np, D = self.n_envs, self.n_pursuers, self.obs_dim
+        _lib.require_tensor(obs0, "obs0", self.dtype, (E, Np, D), self.device)
+        if out is None:
+            obs = torch.empty((T, E, Np, D), dtype=self.dtype, device=self.device)
+            rew = torch.empty((T, E, Np), dtype=self.dtype, device=self.device)
+            done = torch.empty((T, E), dtype=torch.uint8, device=self.device)
+            info = torch.empty((T, E, 2), dtype=torch.int32, device=self.device)
+        else:
+            obs, rew, done, info = self._require_outputs(T, out, self.device)
+        act = torch.empty((T, E, Np, 2), dtype=self.dtype, device=self.device) if record_actions else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.madrl_ww_rollout_heuristic(self._h, T, _ptr(obs0), _ptr(act), _ptr(obs), _ptr(rew),
+                                                          _ptr(done), _ptr(info), int(auto_reset), self._stream()))
+        return act, obs, rew, done, info
+
     def step(self, actions, auto_reset=False):
         """One lockstep step.  actions [E, Np, 2] (or anything reshapeable to it)."""
         a = torch.as_tensor(actions, device=self.device, dtype=self.dtype).reshape(

@@ -283,3 +283,37 @@ def load_rltools_samplers():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_reference_heuristics():
+    """heuristics/waterworld.py and heuristics/pursuit.py loaded from their files, with ``rltools.policy.Policy``
+    (a TensorFlow ``nn.Model`` subclass, rltools/rltools/policy/__init__.py:4-22) replaced by a stub that keeps
+    the two spaces.  Returns (WaterworldHeuristicPolicy, PursuitHeuristicPolicy, pursuit_source) -- the source
+    text lets a test re-evaluate heuristics/pursuit.py:23 `xs / 2` with Python 2's integer division."""
+    install()
+    import importlib.util
+    rl = sys.modules["rltools"]
+
+    class Policy(object):
+        def __init__(self, observation_space, action_space):
+            self._observation_space, self._action_space = observation_space, action_space
+
+        @property
+        def observation_space(self):
+            return self._observation_space
+
+        @property
+        def action_space(self):
+            return self._action_space
+
+    rl.policy = _module("rltools.policy", Policy=Policy)
+    out = []
+    for name in ("waterworld", "pursuit"):
+        path = os.path.join(REFERENCE_ROOT, "heuristics", name + ".py")
+        spec = importlib.util.spec_from_file_location("_ref_heuristics_" + name, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        out.append(mod)
+    with open(os.path.join(REFERENCE_ROOT, "heuristics", "pursuit.py")) as f:
+        src = f.read()
+    return out[0].WaterworldHeuristicPolicy, out[1].PursuitHeuristicPolicy, src

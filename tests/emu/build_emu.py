@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "madrl_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-SOURCES = ["common.cu", "waterworld.cu", "pursuit.cu", "hostage.cu", "postproc.cu"]
+SOURCES = ["common.cu", "waterworld.cu", "pursuit.cu", "hostage.cu", "postproc.cu", "heuristics.cu"]
 # postproc.cu: its shared arrays are block-static, not `extern`; the fixed reduction grid (592 blocks of
 # 256 threads on the GPU) is narrowed so that a launch does not create 150 000 fibers
 PER_FILE_FLAGS = {"postproc.cu": ["-D__shared__=static", "-DMADRL_MOM_BLOCKS=6"]}

@@ -51,6 +51,8 @@ def _declare(lib):
         g("rollout").argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp]
         g("rollout_host").argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
         g("reset_host").argtypes = [vp, vp, vp]
+    lib.madrl_ww_rollout_heuristic.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, vp]
+    lib.madrl_pursuit_rollout_heuristic.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp]
 
 
 def _p(a):
@@ -130,8 +132,48 @@ class _Engine(object):
         return tuple(b.check(n) for b, n in zip(bufs, ("obs", "rew", "done", "info")))
 
 
+    def rollout_heuristic(self, T, obs0, auto_reset=True, **kw):
+        """Closed-loop rollout with the in-kernel heuristic policy -> (actions, obs, rew, done, info)."""
+        E, A = self.n_envs, self.n_agents
+        obs0 = np.ascontiguousarray(obs0, self.obs_dtype)
+        assert obs0.shape == (E, A, self.obs_dim)
+        bufs = [Guarded((T, E, A) + self.act_shape, self.act_dtype, -7),
+                Guarded((T, E, A, self.obs_dim), self.obs_dtype, np.nan), Guarded((T, E, A), self.obs_dtype, np.nan),
+                Guarded((T, E), np.uint8, 255), Guarded((T, E) + self.info_shape, np.int32, -1)]
+        ptrs = [_p(b.arr) for b in bufs]
+        extra = [int(bool(kw.get("py2_division", True)))] if self.fam == "pursuit" else []
+        self._check(self._f("rollout_heuristic")(self._h, T, _p(obs0), *ptrs, int(auto_reset), *extra, None))
+        return tuple(b.check(n) for b, n in zip(bufs, ("actions", "obs", "rew", "done", "info")))
+
+
+def ww_heuristic_actions(obs, n_sensors, defines=()):
+    """madrl_ww_heuristic_actions through the emulator: obs [n, D] float32 / float64 -> actions [n, 2]."""
+    lib = load(defines)
+    lib.madrl_ww_heuristic_actions.argtypes = [C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    obs = np.ascontiguousarray(obs)
+    out = Guarded((obs.shape[0], 2), obs.dtype, np.nan)
+    rc = lib.madrl_ww_heuristic_actions(int(obs.dtype == np.float64), obs.shape[0], n_sensors, obs.shape[1], _p(obs),
+                                        _p(out.arr), None)
+    assert rc == 0, lib.madrl_last_error().decode()
+    return out.check("actions")
+
+
+def pursuit_heuristic_actions(obs, obs_range, flatten, fallback, py2_division=True, defines=()):
+    """madrl_pursuit_heuristic_actions through the emulator: obs [n, D] float32 -> actions [n] int32."""
+    lib = load(defines)
+    lib.madrl_pursuit_heuristic_actions.argtypes = [C.c_size_t] + [C.c_int] * 4 + [C.c_void_p] * 5
+    obs = np.ascontiguousarray(obs, np.float32)
+    fb = np.ascontiguousarray(fallback, np.int32)
+    lut = np.zeros(128, np.uint8)
+    out = Guarded((obs.shape[0],), np.int32, -9)
+    rc = lib.madrl_pursuit_heuristic_actions(obs.shape[0], obs_range, int(flatten), obs.shape[1], int(py2_division),
+                                             _p(obs), _p(fb), _p(lut), _p(out.arr), None)
+    assert rc == 0, lib.madrl_last_error().decode()
+    return out.check("actions")
+
+
 class EmuWaterworld(_Engine):
-    fam, LayoutT, info_shape = "ww", L.WWLayout, (2,)
+    fam, LayoutT, info_shape, act_shape = "ww", L.WWLayout, (2,), (2,)
 
     def __init__(self, n_envs, n_pursuers, n_evaders, n_coop=2, n_poison=10, radius=0.015,
                  obstacle_radius=0.2, obstacle_loc=np.array([0.5, 0.5]), ev_speed=0.01,
@@ -168,7 +210,7 @@ class EmuWaterworld(_Engine):
 
 
 class EmuHostage(_Engine):
-    fam, LayoutT, info_shape = "hostage", L.HWLayout, (2,)
+    fam, LayoutT, info_shape, act_shape = "hostage", L.HWLayout, (2,), (2,)
 
     def __init__(self, n_envs, n_good, n_hostages, n_bad, n_coop_save, n_coop_avoid, radius=0.015,
                  key_loc=None, bad_speed=0.01, n_sensors=30, sensor_range=0.2, action_scale=0.01,
@@ -202,7 +244,7 @@ class EmuHostage(_Engine):
 
 
 class EmuPursuit(_Engine):
-    fam, LayoutT, info_shape = "pursuit", L.PELayout, ()
+    fam, LayoutT, info_shape, act_shape = "pursuit", L.PELayout, (), ()
     obs_dtype, act_dtype = np.float32, np.int32
 
     def __init__(self, n_envs, map_pool, n_evaders=1, n_pursuers=1, obs_range=3, flatten=True,

@@ -155,6 +155,12 @@ static inline unsigned __reduce_or_sync(unsigned, unsigned v) {
   for (int i = 0; i < 32; ++i) m |= (unsigned)s[i];
   return m;
 }
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+  const uint64_t* s = madrl_emu::warp_exchange(v);
+  unsigned m = 0xffffffffu;
+  for (int i = 0; i < 32; ++i) m = (unsigned)s[i] < m ? (unsigned)s[i] : m;
+  return m;
+}
 static inline void __syncwarp(unsigned = 0xffffffffu) { madrl_emu::warp_exchange(0); madrl_emu::note_sync(); }
 static inline void __syncthreads() { madrl_emu::block_barrier(); madrl_emu::note_sync(); }
 
@@ -168,6 +174,7 @@ static inline float fminf_(float a, float b) { return a < b ? a : b; }
 // ---- scalar intrinsics ---------------------------------------------------------------------------
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline unsigned __float_as_uint(float v) { return (unsigned)madrl_emu::to_bits(v); }
 static inline float __int_as_float(int v) { return madrl_emu::from_bits<float>((uint32_t)v); }
 static inline double __longlong_as_double(long long v) { return madrl_emu::from_bits<double>((uint64_t)v); }
 // round-to-nearest, never contracted into an FMA (volatile operands)

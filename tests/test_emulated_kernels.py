@@ -21,6 +21,8 @@ pytestmark = pytest.mark.skipif(shutil.which(os.environ.get("CXX", "g++")) is No
 # build variants: the product defaults (the round-1 experiment flags were measured on the GPU in round 2
 # and either became the default or were deleted, profiles/r2_ab_variants.log)
 VARIANTS = {"default": ()}
+if os.environ.get("MADRL_EMU_DEFINES"):   # ad-hoc check of an experiment build: MADRL_EMU_DEFINES="-DFOO=1 -DBAR=1"
+    VARIANTS["env"] = tuple(os.environ["MADRL_EMU_DEFINES"].split())
 PE_VARIANTS = sorted(VARIANTS)
 
 
