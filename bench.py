@@ -437,6 +437,51 @@ def e2e_of(r, steps, obs_last):
                    % (fam, ", MADRL_HOST_OBS_LAST" if obs_last else "")}
 
 
+def closed_loop_of(r, steps):
+    """Closed-loop rollouts with the reference's hand-written policy evaluated INSIDE the rollout kernel
+    (madrl_ww_rollout_heuristic / madrl_pursuit_rollout_heuristic through the Batched* classes): no action
+    tensor exists at all; per rollout the actions taken, rewards, dones and infos are copied to pinned host
+    memory inside the timed region (what a learner on the host consumes), the observations stay in HBM."""
+    import torch
+    import torch.distributed as dist
+    if not hasattr(r.eng, "rollout_heuristic"):
+        return None
+    E, Np, T = r.E, r.Np, r.T
+    obs0 = r.eng.reset()
+    out = (r.obs_buf, r.packed.rew, r.packed.done, r.packed.info)
+    host = None
+    def one(obs_prev):
+        nonlocal host
+        act, obs, rew, done, info = r.eng.rollout_heuristic(T, obs_prev, auto_reset=True, out=out)
+        if host is None:
+            host = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in (act, rew, done, info)]
+        for h, x in zip(host, (act, rew, done, info)):
+            h.copy_(x, non_blocking=True)
+        return obs[-1]
+    prev = obs0
+    for _ in range(2):
+        prev = one(prev)
+    if r.world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n = max(3, min(steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        prev = one(prev)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if r.world > 1:
+        t = torch.tensor([dt], device=r.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    d2h = int(sum(h.numel() * h.element_size() for h in host))
+    return {"value": r.world * E * Np * T * n / dt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
+            "t_inner": T, "api": "Batched%s.rollout_heuristic (policy of heuristics/%s.py in the rollout kernel; actions, "
+                                 "rewards, dones, infos copied to pinned host memory per rollout)"
+                                 % ({"ww": "MAWaterWorld", "pe": "PursuitEvade"}[r.W["family"]],
+                                    {"ww": "waterworld", "pe": "pursuit"}[r.W["family"]])}
+
+
 def pcie_d2h_gbs(dev):
     """Live pinned device->host copy rate of this box (the ceiling of the full-observation e2e)."""
     import torch
@@ -545,6 +590,9 @@ def main():
         e2e["policy_on_device"] = dict(lite, note="MADRL_HOST_OBS_LAST: rewards / dones / infos of every step + "
                                        "the last observations return to the host; the per-step observations "
                                        "stay in HBM for a policy that runs on the GPU")
+        cl = closed_loop_of(r, a.steps)
+        if cl is not None:
+            e2e["closed_loop_heuristic"] = cl
     r.close()
 
     # ---- the other BASELINE configs, short (5 steps each) ------------------------------------------

@@ -102,6 +102,9 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
 __device__ __forceinline__ void reds_add_u32(uint32_t a, uint32_t v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+__device__ __forceinline__ void reds_min_u32(uint32_t a, uint32_t v) {
+  asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 // Staged sensing candidate in shared memory (one slot per object that survives the range cull):
 // {rx, ry, d2} = position relative to the sensing agent and its squared norm, {vx, vy} = velocity.
 // 32-bit shared addresses, vector accesses: one broadcast load per candidate in the sensor loops.

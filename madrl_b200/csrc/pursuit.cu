@@ -17,8 +17,13 @@
 //     rollout and in HBM between launches.
 //   * Evader actions: live evader with live-rank r takes draw (ctr + r) of the env's Philox
 //     stream (ct:16 one randint(5) per live evader, in order) -- computed by all lanes at once.
-//   * Observation rows are written cell-major: lane w handles window cell w for all 3 channels
-//     (shared coordinate math), three coalesced stores per 32 cells.
+//   * The grid carries a border of off+1 marker cells (bit 31), so a window cell needs no bounds test:
+//     its word address is (pursuer cell) + (a per-lane constant), and "out of bounds" is one bit of the
+//     word.  Observation rows are written cell-major: lane w handles window cell w for all 3 channels,
+//     three coalesced stores per 32 cells.  (Walking the cells of ALL pursuers as one flat list, 12.25
+//     full rounds instead of 8 x 2 half-empty ones, was built and measured in SASS: 51 instructions per
+//     round against 60 per pursuer here -- the per-pursuer form shares its shuffles and loop overhead
+//     between two cells per lane.)
 #include <math.h>
 #include <string.h>
 #include <new>
@@ -34,7 +39,8 @@ struct PEParams {
   int n_catch, surround, reward_global, include_id, sample_maps, max_path_length, flatten, max_opponents;
   int T, mode, auto_reset;
   size_t obs_step, agent_step;    // element strides of one lockstep step: E*Np*D and E*Np
-  int smem_per_warp, cells_pad;   // bytes of shared memory per warp; xs*ys rounded up to 32
+  int smem_per_warp, cells_pad;   // bytes of shared memory per warp; padded grid cells rounded up to 32
+  int pad, ysP, ncellP;           // border width (off + 1), padded row length ys + 2 pad, padded cell count
   double constraint_window, catchr, term_pursuit, urgency;
   float wall_val, one_val;        // float32(1/layer_norm) the two ways the reference gets it
   uint64_t seed;
@@ -106,19 +112,27 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
   // shared memory: block-wide count->value table, then per warp: cell words, stale window counts
   for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<float*>(smem_u32)[i] = p.lut[i];
   __syncthreads();   // the only block barrier: once, before the persistent loop
-  const uint32_t lut_a = smem_addr(smem_u32);
-  const uint32_t cell_a = lut_a + 1024u + (uint32_t)wib * (uint32_t)p.smem_per_warp;
+  uint32_t lut_a = smem_addr(smem_u32);
+  uint32_t cell_a = lut_a + 1024u + (uint32_t)wib * (uint32_t)p.smem_per_warp;
+  // keep both in registers: ptxas otherwise re-derives them from SR_CgaCtaId in front of every shared access
+  asm volatile("" : "+r"(lut_a), "+r"(cell_a));
   const uint32_t stale_a = cell_a + 4u * (uint32_t)p.cells_pad;
   const uint32_t wcache_a = cell_a + (uint32_t)p.smem_per_warp - 512u;   // last 512 bytes of the warp's region
+  // map cell (x, y) lives at cell0 + 4 (x ysP + y): a border of `pad` marker cells surrounds the map
+  const int ysP = p.ysP;
+  const uint32_t cell0 = cell_a + 4u * (uint32_t)(p.pad * ysP + p.pad);
+  constexpr uint32_t BORDER = 0x80000001u;   // bit 31 = outside the map; byte 0 = 1: nobody moves there
   const float my_idv = (lane < p.Np) ? p.idv[lane] : 0.0f;   // lane i keeps float32(i / Np)
 
-  // per-lane window cell offsets
-  int wdx[CPL], wdy[CPL];
+  // per-lane window cells: local_obs[i, ch, wx, wy] <-> map cell (x - off + wx, y - off + wy) (pe:430-438), as a byte
+  // offset from the pursuer's cell in the bordered grid; bit 31 = not a window cell of this lane / a cell of an even
+  // window beyond 2*off, which the reference never writes
+  uint32_t woff[CPL];
 #pragma unroll
   for (int it = 0; it < CPL; ++it) {
-    const int w = lane + 32 * it;
-    wdx[it] = w / R - p.off;   // local_obs[i, ch, wx, wy] <-> map cell (x - off + wx, y - off + wy)
-    wdy[it] = w % R - p.off;
+    const int w = lane + 32 * it, wdx = w / R - p.off, wdy = w % R - p.off;
+    const bool cell = w < RR && wdx <= p.off && wdy <= p.off;
+    woff[it] = cell ? 4u * (uint32_t)((wdx + p.pad) * ysP + (wdy + p.pad)) : 0x80000000u;
   }
   const int n_tail = p.include_id ? 1 : 0;
   // POLICY: sort key of window cell w as "nearest visible evader" (heuristics/pursuit.py:28-31): squared
@@ -232,12 +246,16 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
         }
         if (rebuild) {   // cell words from scratch: building flag + occupancy counts
           __syncwarp();
-          for (int i = lane; i < ncell; i += 32) sts_u32(cell_a + 4u * i, map[i] ? 1u : 0u);
+          for (int i = lane; i < p.ncellP; i += 32) {
+            const int X = i / ysP, x = X - p.pad, y = i - X * ysP - p.pad;
+            const bool in = (unsigned)x < (unsigned)xs && (unsigned)y < (unsigned)ys;
+            sts_u32(cell_a + 4u * i, in ? (map[x * ys + y] ? 1u : 0u) : BORDER);
+          }
           __syncwarp();
-          if (lane < Np) reds_add_u32(cell_a + 4u * (px * ys + py), 1u << 8);
+          if (lane < Np) reds_add_u32(cell0 + 4u * (px * ysP + py), 1u << 8);
 #pragma unroll
           for (int c = 0; c < EPL; ++c)
-            if ((live[c] >> lane) & 1u) reds_add_u32(cell_a + 4u * (ex[c] * ys + ey[c]), 1u << 16);
+            if ((live[c] >> lane) & 1u) reds_add_u32(cell0 + 4u * (ex[c] * ysP + ey[c]), 1u << 16);
           __syncwarp();
           rebuild = false;
         }
@@ -246,10 +264,10 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
           if (lane < Np) {
             const int xm = max(px - 1, 0), xp = min(px + 1, xs - 1);
             const int ym = max(py - 1, 0), yp = min(py + 1, ys - 1);
-            rcount = (int)((lds_u32(cell_a + 4u * (xm * ys + py)) >> 16) & 0xff) +
-                     (int)((lds_u32(cell_a + 4u * (xp * ys + py)) >> 16) & 0xff) +
-                     (int)((lds_u32(cell_a + 4u * (px * ys + yp)) >> 16) & 0xff) +
-                     (int)((lds_u32(cell_a + 4u * (px * ys + ym)) >> 16) & 0xff);
+            rcount = (int)((lds_u32(cell0 + 4u * (xm * ysP + py)) >> 16) & 0xff) +
+                     (int)((lds_u32(cell0 + 4u * (xp * ysP + py)) >> 16) & 0xff) +
+                     (int)((lds_u32(cell0 + 4u * (px * ysP + yp)) >> 16) & 0xff) +
+                     (int)((lds_u32(cell0 + 4u * (px * ysP + ym)) >> 16) & 0xff);
           }
           __syncwarp();
           // ---- move pursuers: pe:227-235, da:69-97 ---------------------------------------------
@@ -257,7 +275,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
             const int a = act;
             const int dx = (a == 0) ? -1 : (a == 1 ? 1 : 0), dy = (a == 2) ? 1 : (a == 3 ? -1 : 0);
             const int nx = px + dx, ny = py + dy;
-            const uint32_t cur = cell_a + 4u * (px * ys + py), nxt = cell_a + 4u * (nx * ys + ny);
+            const uint32_t cur = cell0 + 4u * (px * ysP + py), nxt = cell0 + 4u * (nx * ysP + ny);
             if ((unsigned)a < 4u && (unsigned)nx < (unsigned)xs && (unsigned)ny < (unsigned)ys &&
                 lds_low_byte(cur) == 0u && lds_low_byte(nxt) == 0u) {
               reds_add_u32(cur, 0u - (1u << 8));
@@ -292,7 +310,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
               const int a = u32_to_range(word, 0, 5);
               const int dx = (a == 0) ? -1 : (a == 1 ? 1 : 0), dy = (a == 2) ? 1 : (a == 3 ? -1 : 0);
               const int nx = ex[c] + dx, ny = ey[c] + dy;
-              const uint32_t cur = cell_a + 4u * (ex[c] * ys + ey[c]), nxt = cell_a + 4u * (nx * ys + ny);
+              const uint32_t cur = cell0 + 4u * (ex[c] * ysP + ey[c]), nxt = cell0 + 4u * (nx * ysP + ny);
               if (a < 4 && (unsigned)nx < (unsigned)xs && (unsigned)ny < (unsigned)ys &&
                   lds_low_byte(cur) == 0u && lds_low_byte(nxt) == 0u) {
                 reds_add_u32(cur, 0u - (1u << 16));
@@ -319,7 +337,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
                 for (int m = 0; m < 4; ++m) {
                   const int xn = x + (m == 0 ? -1 : (m == 1 ? 1 : 0)), yn = y + (m == 2 ? 1 : (m == 3 ? -1 : 0));
                   if ((unsigned)xn < (unsigned)xs && (unsigned)yn < (unsigned)ys) {
-                    const uint32_t wv = lds_u32(cell_a + 4u * (xn * ys + yn));
+                    const uint32_t wv = lds_u32(cell0 + 4u * (xn * ysP + yn));
                     if ((wv >> 8) & 0xff) adj += 1;
                     // pe:536 skips neighbours with xn <= 0 or yn <= 0: row/column 0 never subtracts
                     if (xn > 0 && yn > 0 && (wv & 0xff)) need -= 1;
@@ -327,7 +345,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
                 }
                 got = (adj == need);
               } else {
-                got = (int)((lds_u32(cell_a + 4u * (x * ys + y)) >> 8) & 0xff) >= p.n_catch;   // pe:498
+                got = (int)((lds_u32(cell0 + 4u * (x * ysP + y)) >> 8) & 0xff) >= p.n_catch;   // pe:498
               }
             }
             caught[c] = __ballot_sync(FULL_MASK, got);
@@ -345,30 +363,27 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
         // ---- collect_obs: pe:418-461 (flatten): channel-major, then x, then y, then id ----------
         {
           float* row = obs_t;
-          uint32_t st_row = stale_a;
+          uint32_t st_row = stale_a + 2u * lane;
           for (int i = 0; i < Np; ++i, row += p.D, st_row += 2u * RR) {
             const int pxi = __shfl_sync(FULL_MASK, px, i), pyi = __shfl_sync(FULL_MASK, py, i);
-            const float idval = __shfl_sync(FULL_MASK, my_idv, i);
+            const uint32_t pcell = cell_a + 4u * (uint32_t)(pxi * ysP + pyi);   // + woff: this lane's window cells
             // explicit software pipeline over the (unrolled) window chunks: all shared loads
             // first, then the dependent table lookups, then the coalesced stores
             uint32_t wv[CPL], c12[CPL];
             bool inb[CPL];
 #pragma unroll
             for (int it = 0; it < CPL; ++it) {
-              const int w = lane + 32 * it;
-              const int cx = pxi + wdx[it], cy = pyi + wdy[it];
-              // cells beyond 2*off (even obs_range) are never written: treated as out of bounds
-              inb[it] = w < RR && (unsigned)cx < (unsigned)xs && (unsigned)cy < (unsigned)ys &&
-                        wdx[it] <= p.off && wdy[it] <= p.off;
-              wv[it] = inb[it] ? lds_u32(cell_a + 4u * (cx * ys + cy)) : 0u;
-              c12[it] = (w < RR) ? lds_u16(st_row + 2u * w) : 0u;       // stale pursuer | evader << 8
+              // the border marker (bit 31 of the word) replaces the four bounds tests; lanes past the window and
+              // the never-written cells of an even window carry the same bit in their constant
+              wv[it] = lds_u32(pcell + (woff[it] & 0x7fffffffu));
+              inb[it] = ((wv[it] | woff[it]) >> 31) == 0u;
+              c12[it] = (lane + 32 * it < RR) ? lds_u16(st_row + 64u * it) : 0u;   // stale pursuer | evader << 8
             }
             float v1[CPL], v2[CPL];
 #pragma unroll
             for (int it = 0; it < CPL; ++it) {
-              const int w = lane + 32 * it;
               if (inb[it]) c12[it] = (wv[it] >> 8) & 0xffffu;
-              if (w < RR) sts_u16(st_row + 2u * w, c12[it]);
+              if (lane + 32 * it < RR) sts_u16(st_row + 64u * it, c12[it]);
               v1[it] = lds_f32(lut_a + 4u * (c12[it] & 0xffu));         // float32(k) / float32(layer_norm)
               v2[it] = lds_f32(lut_a + 4u * (c12[it] >> 8));
             }
@@ -396,6 +411,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
             } else {
               // flatten=False: np.rollaxis(local_obs[i], 0, 3) -> [x][y][channel], channel 3 holds
               // i/Np at the window centre and zeros elsewhere (pe:440-449): one 16-byte store per cell
+              const float idval = __shfl_sync(FULL_MASK, my_idv, i);
               const int centre = (R / 2) * R + (R / 2);
 #pragma unroll
               for (int it = 0; it < CPL; ++it) {
@@ -406,8 +422,8 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
                 }
               }
             }
-            if (p.flatten && lane < n_tail) store_stream(row + 3 * RR, idval);              // pe:444-445
           }
+          if (p.flatten && n_tail && lane < Np) store_stream(obs_t + (size_t)lane * p.D + 3 * RR, my_idv);   // pe:444-445
         }
         need_reset = false;
         if (!pass) {
@@ -431,7 +447,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
           int n_live = 0;
 #pragma unroll
           for (int c = 0; c < EPL; ++c) {
-            if ((caught[c] >> lane) & 1u) reds_add_u32(cell_a + 4u * (ex[c] * ys + ey[c]), 0u - (1u << 16));
+            if ((caught[c] >> lane) & 1u) reds_add_u32(cell0 + 4u * (ex[c] * ysP + ey[c]), 0u - (1u << 16));
             live[c] &= ~caught[c];
             n_live += __popc(live[c]);
           }
@@ -524,6 +540,7 @@ extern "C" int madrl_pursuit_state_layout(const madrl_pursuit_config* c, madrl_p
   out->maps = take((size_t)c->n_maps * c->xs * c->ys);
   out->lut = take(4 * 256);
   out->idv = take(4 * 32);
+
   out->total_bytes = off;
   out->n_agents = (int32_t)Nag;
   out->obs_dim = c->flatten ? (int32_t)(3 * RR + (c->include_id ? 1 : 0))   // pe:108-112
@@ -566,6 +583,7 @@ extern "C" int madrl_pursuit_create(const madrl_pursuit_config* c, const int32_t
   delete[] m8;
   if (e == cudaSuccess) e = cudaMemcpy(h->state + lay.lut, lut, sizeof(lut), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->state + lay.idv, idv, sizeof(idv), cudaMemcpyHostToDevice);
+
   if (e != cudaSuccess) { set_error("cudaMemcpy(tables): %s", cudaGetErrorString(e)); madrl_pursuit_destroy(h); return MADRL_ECUDA; }
   *out = h;
   return MADRL_OK;
@@ -675,8 +693,9 @@ static int pe_launch(madrl_pursuit* h, int mode, int T, const int32_t* actions, 
   p.flatten = c.flatten;
   p.T = T; p.mode = mode; p.auto_reset = auto_reset;
   p.obs_step = (size_t)p.E * p.Np * p.D; p.agent_step = (size_t)p.E * p.Np;
-  const int ncell = c.xs * c.ys, RR = c.obs_range * c.obs_range;
-  p.cells_pad = (ncell + 31) / 32 * 32;
+  const int RR = c.obs_range * c.obs_range;
+  p.pad = p.off + 1; p.ysP = c.ys + 2 * p.pad; p.ncellP = (c.xs + 2 * p.pad) * p.ysP;
+  p.cells_pad = (p.ncellP + 31) / 32 * 32;
   p.smem_per_warp = (int)align_up((size_t)p.cells_pad * 4 + (size_t)c.n_pursuers * RR * 2, 16) +
                     512;   // + the warp's Philox word cache
   p.constraint_window = c.constraint_window; p.catchr = c.catchr; p.term_pursuit = c.term_pursuit;

@@ -184,6 +184,7 @@ static inline double __ddiv_rn(double a, double b) { volatile double x = a, y = 
 template <typename T> static inline void __stcs(T* p, T v) { *p = v; }
 template <typename T> static inline T __ldcs(const T* p) { return *p; }
 template <typename T> static inline T __ldcg(const T* p) { return *p; }
+template <typename T> static inline T __ldg(const T* p) { return *p; }
 
 // ---- host versions of the PTX-level helpers of csrc/common.cuh -------------------------------------
 #define MADRL_EMU_PTX_HELPERS 1
@@ -200,6 +201,10 @@ static inline float lds_f32(uint32_t a) { smem_access(a, 4, SMEM_READ); float v;
 static inline uint32_t lds_u16(uint32_t a) { smem_access(a, 2, SMEM_READ); uint16_t v; memcpy(&v, emu_at(a), 2); return v; }
 static inline void sts_u32(uint32_t a, uint32_t v) { smem_access(a, 4, SMEM_WRITE); memcpy(emu_at(a), &v, 4); }
 static inline void sts_u16(uint32_t a, uint32_t v) { smem_access(a, 2, SMEM_WRITE); const uint16_t h = (uint16_t)v; memcpy(emu_at(a), &h, 2); }
+static inline void reds_min_u32(uint32_t a, uint32_t v) {
+  smem_access(a, 4, SMEM_ATOMIC);
+  uint32_t w; memcpy(&w, emu_at(a), 4); w = v < w ? v : w; memcpy(emu_at(a), &w, 4);
+}
 static inline void reds_add_u32(uint32_t a, uint32_t v) {
   const uint32_t first = v ? (uint32_t)__builtin_ctz(v) / 8u : 0u;   // bytes below the lowest set bit of v never change
   smem_access(a + first, 4 - first, SMEM_ATOMIC);
