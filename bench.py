@@ -375,7 +375,11 @@ def time_runner(r, steps, warmup, sampler=None):
     launches = launch_count() - l0
     ms = ev0.elapsed_time(ev1)
     kern_ms = float(np.mean([s.elapsed_time(e) for s, e in kev]))
+    r.kernel_ms_per_rank = [kern_ms]
     if r.world > 1:
+        per = torch.zeros(r.world, device=r.dev)
+        dist.all_gather_into_tensor(per, torch.tensor([kern_ms], device=r.dev))
+        r.kernel_ms_per_rank = [float(x) for x in per.tolist()]
         t = torch.tensor([ms, kern_ms], device=r.dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, kern_ms = float(t[0].item()), float(t[1].item())
@@ -577,6 +581,18 @@ def main():
     agent_steps_per_step = world * E * WL["agents"] * T * LAUNCHES_PER_STEP
     value = agent_steps_per_step * a.steps / (ms * 1e-3)
     mode, note, completion = r.mode, r.note, getattr(r, "completion", None)
+    # where a multi-GPU run loses time: the rollout kernel's mean duration on every rank with the per-rollout
+    # exchange running behind it, and again with the exchange switched off (same engines, same actions)
+    probe = None
+    if world > 1:
+        probe = {"kernel_ms_per_rank": r.kernel_ms_per_rank}
+        keep = (r.agather, r.mode, r.k)
+        r.agather, r.mode = None, "none"
+        time_runner(r, 5, 1)
+        probe["kernel_ms_per_rank_no_exchange"] = r.kernel_ms_per_rank
+        r.agather, r.mode, r.k = keep          # the exchange's sequence numbers continue where they stopped
+        probe["note"] = ("mean rollout-kernel duration per rank (CUDA events around each launch); `value` uses the "
+                         "max over ranks, so rank-to-rank spread of the GPUs costs efficiency even without an exchange")
 
     # ---- e2e through the host-buffer C ABI ----------------------------------------------------------
     e2e = None
@@ -690,6 +706,8 @@ def main():
         line["workloads"] = extra
     if full:
         line["full_gather"] = full
+    if probe:
+        line["scaling_probe"] = probe
     if world == 1 and not a.no_cpu:
         procs = host_cores
         v = cpu_baseline(a.cpu_seconds, procs, a.workload)

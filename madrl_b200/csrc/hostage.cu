@@ -127,12 +127,18 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
     int pass = (p.mode == 1) ? 1 : 0;
     const V2* act_t = reinterpret_cast<const V2*>(p.actions) + (size_t)e * p.Nr + lane;
 
+    V2 act_nx;
+    act_nx.x = 0; act_nx.y = 0;
+    if (p.mode == 0 && lane < p.Nr) act_nx = *act_t;
     for (int t = 0; t < p.T; ++t) {
       V2 act;
       act.x = 0; act.y = 0;
       if (p.mode == 0 && lane < p.Nr) {
-        act = *act_t;
-        if (t + 1 < p.T) prefetch_l1(act_t + p.agent_step);   // next step's action -> L1
+        // double-buffered in registers: the load for step t+1 is issued at the top of step t, so its HBM
+        // latency hides behind a whole step (prefetch.global.L1 did not: the first use of the action was 10 % of
+        // all stall samples of the C2 kernel; C2 66 -> 74.5 % of the roofline, profiles/r2_ab_action_db.log)
+        act = act_nx;
+        if (t + 1 < p.T) act_nx = act_t[p.agent_step];
       }
       bool need_reset;
       do {

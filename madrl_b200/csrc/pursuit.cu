@@ -192,6 +192,8 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
                                         : u32_to_range(stream_word(p.seed, env_id, PE_POLICY_TAG, ctr * 32u + (uint64_t)i), 0, 5);
       }
     }
+    int act_nx = 4;
+    if (!POLICY && p.mode == 0 && lane < Np) act_nx = *act_t;
     for (int t = 0; t < p.T; ++t) {
       int act = 4;
       if constexpr (POLICY) {
@@ -200,8 +202,11 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
           if (p.actions_out != nullptr) p.actions_out[(size_t)t * p.agent_step + (size_t)e * Np + lane] = act;
         }
       } else if (p.mode == 0 && lane < Np) {
-        act = *act_t;
-        if (t + 1 < p.T) prefetch_l1(act_t + p.agent_step);   // next step's action -> L1
+        // double-buffered in registers: the load for step t+1 is issued at the top of step t, so its HBM
+        // latency hides behind a whole step (prefetch.global.L1 did not: the first use of the action was 10 % of
+        // all stall samples of the C2 kernel; C2 66 -> 74.5 % of the roofline, profiles/r2_ab_action_db.log)
+        act = act_nx;
+        if (t + 1 < p.T) act_nx = act_t[p.agent_step];
       }
       bool need_reset;
       do {
