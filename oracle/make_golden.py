@@ -197,12 +197,98 @@ def gen_hostage(ContinuousHostageWorld):
         print(name, "saved/encs", np.array(info).sum(0), "dones", int(np.sum(done)), "draws", env.np_random.counter)
 
 
+CL_WW_CASES = {
+    # name: (ctor kwargs, seed, env_id, T)
+    "cl_ww_c2": (dict(n_pursuers=5, n_evaders=5), 41, 17, 150),
+    # seed chosen so that no decision normalises a rounding residue: with seed 42 two pursuers sense equal distances
+    # in opposite directions at step 44, the weighted sum is 2e-18 instead of 0 and the reference policy turns that
+    # noise into a unit action -- reproducible only with bit-identical observations (min_norm is recorded below)
+    "cl_ww_dense": (dict(n_pursuers=4, n_evaders=6, n_poison=6, n_coop=1, radius=0.04, sensor_range=0.3), 45, 2, 150),
+}
+CL_PE_CASES = {
+    # name: (map source, ctor kwargs (flatten=False: the policy reads the (R, R, 4) layout), seed, env_id, T, py2 division)
+    "cl_pe_conv_py2": ("pool16", dict(PE_C3, flatten=False, n_evaders=12, obs_range=7), 43, 11, 120, True),
+    "cl_pe_conv_py3": ("pool16", dict(PE_C3, flatten=False, n_evaders=12, obs_range=7), 43, 11, 120, False),
+    "cl_pe_sparse_py2": ("pool16", dict(PE_C3, flatten=False, n_evaders=3, n_pursuers=6, obs_range=5, surround=False,
+                                        n_catch=1), 44, 12, 150, True),
+}
+
+
+def gen_closed_loop(MAWaterWorld):
+    """CLOSED LOOP of the real reference: the reference env stepped with the actions of the reference's own
+    hand-written policy (heuristics/waterworld.py, heuristics/pursuit.py), called per agent as the reference's
+    Visualizer does.  The engine's in-kernel policy rollouts (madrl_*_rollout_heuristic) must reproduce these
+    trajectories.  Pursuit: `action_space.sample()` is the injected policy stream of oracle/heuristics_oracle.py;
+    py2 = line 23's `xs / 2, ys / 2` spelt `//` (what it means in the reference's Python 2)."""
+    import types
+    from oracle.heuristics_oracle import policy_draw
+    from oracle.refshim import REFERENCE_ROOT, load_reference_heuristics, make_reference_pursuit
+    WPol, PPol, psrc = load_reference_heuristics()
+    for name, (kw, seed, env_id, T) in CL_WW_CASES.items():
+        env = MAWaterWorld(**kw)
+        env.np_random = Stream(seed, env_id)
+        pol = WPol(env.agents[0].observation_space, env.agents[0].action_space)
+        o = env.reset()
+        obs0 = np.array(o)
+        acts, obs, rew, info, min_norm = [], [], [], [], np.inf
+        from oracle.heuristics_oracle import waterworld_action
+        for t in range(T):
+            a = np.array([pol.sample_actions(np.asarray(oi)[None])[0][0] for oi in o])
+            norms = [waterworld_action(np.asarray(oi), True)[1] for oi in o]
+            min_norm = min([min_norm] + [x for x in norms if x > 0])
+            o, r, d, i = env.step(a)
+            acts.append(a); obs.append(np.array(o)); rew.append(np.array(r)); info.append([i['evcatches'], i['pocatches']])
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), config=json.dumps(kw), seed=seed, env_id=env_id,
+                            obs0=obs0, actions=np.array(acts), obs=np.array(obs), rew=np.array(rew),
+                            info=np.array(info, dtype=np.int32), counter=env.np_random.counter, min_norm=min_norm)
+        assert min_norm > 1e-6, "ill-conditioned closed loop (a rounding residue is normalised): pick another seed"
+        print(name, "catches", np.array(info).sum(0), "moving", float(np.mean(np.linalg.norm(acts, axis=-1) > 0)),
+              "min un-normalised norm", min_norm)
+    pool16 = np.load(os.path.join(REFERENCE_ROOT, "maps", "map_pool16.npy"))
+    ported = psrc.replace("x, y = xs / 2, ys / 2", "x, y = xs // 2, ys // 2")
+    assert ported != psrc
+    mod2 = types.ModuleType("_ref_heuristics_pursuit_py2")
+    exec(compile(ported.split("if __name__")[0], "heuristics/pursuit.py[py2 division]", "exec"), mod2.__dict__)
+
+    class _Space(object):
+        def sample(self):
+            return self.draw()
+
+    for name, (msrc, kw, seed, env_id, T, py2) in CL_PE_CASES.items():
+        maps = pool16 if msrc == "pool16" else small_map()
+        stream = Stream(seed, env_id)
+        env = make_reference_pursuit(maps, stream, **kw)
+        space = _Space()
+        pol = (mod2.PursuitHeuristicPolicy if py2 else PPol)(None, space)
+        o = env.reset()
+        obs0 = np.array(o)
+        acts, obs, rew, done, removed, sampled = [], [], [], [], [], 0
+        for t in range(T):
+            a = []
+            for q, oq in enumerate(o):
+                hit = []
+                space.draw = lambda q=q: hit.append(1) or policy_draw(seed, env_id, stream.counter, q)
+                a.append(int(pol.sample_actions(np.asarray(oq))[0]))
+                sampled += len(hit)
+            o, r, d, i = env.step(a)
+            acts.append(a); obs.append(np.array(o)); rew.append(np.asarray(r, dtype=np.float64)); done.append(d)
+            removed.append(i['removed'])
+            if d:
+                break
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), config=json.dumps(kw), maps=msrc, seed=seed,
+                            env_id=env_id, py2=py2, obs0=obs0, actions=np.array(acts, dtype=np.int32),
+                            obs=np.array(obs), rew=np.array(rew), done=np.array(done),
+                            removed=np.array(removed, dtype=np.int32), counter=stream.counter)
+        print(name, "steps", len(acts), "removed", int(np.sum(removed)), "sampled actions", sampled)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     MAWaterWorld, PursuitEvade, ContinuousHostageWorld = load_reference()
     gen_waterworld(MAWaterWorld)
     gen_pursuit()
     gen_hostage(ContinuousHostageWorld)
+    gen_closed_loop(MAWaterWorld)
 
 
 if __name__ == "__main__":

@@ -287,3 +287,56 @@ def test_emulated_pursuit_generator_matches_oracle(py2):
         assert list(pursuit_heuristic_actions(conv.reshape(n, -1), R, False, fb, py2)) == want
         assert list(pursuit_heuristic_actions(flat, R, True, fb, py2)) == want
         assert any(w == f and not win[i].any() for i, (w, f) in enumerate(zip(want, fb)))
+
+
+# ------------------------------------------------------------------------------ closed-loop goldens
+# tests/golden/cl_*.npz: the REAL reference env stepped by the REAL reference policy (oracle/make_golden.py
+# gen_closed_loop).  The engine's in-kernel policy rollout must reproduce the whole trajectory.
+import json  # noqa: E402
+
+from conftest import GOLDEN_DIR  # noqa: E402
+
+CL_WW = ["cl_ww_c2", "cl_ww_dense"]
+CL_PE = ["cl_pe_conv_py2", "cl_pe_conv_py3", "cl_pe_sparse_py2"]
+
+
+def check_closed_loop_golden_ww(g, reset, rollout, tol):
+    obs0 = reset()
+    assert np.abs(obs0[0] - g["obs0"]).max() < tol
+    act, obs, rew, done, info = rollout(len(g["actions"]), obs0)
+    assert np.abs(act[:, 0] - g["actions"]).max() < tol
+    assert np.abs(obs[:, 0] - g["obs"]).max() < tol and np.abs(rew[:, 0] - g["rew"]).max() < tol
+    assert np.array_equal(info[:, 0], g["info"]) and not done.any()
+
+
+def check_closed_loop_golden_pe(g, reset, rollout):
+    obs0 = reset()
+    assert np.array_equal(obs0[0], f32(g["obs0"]).reshape(obs0[0].shape))
+    T = len(g["actions"])
+    act, obs, rew, done, removed = rollout(T, obs0)
+    assert np.array_equal(act[:, 0], g["actions"])
+    assert np.array_equal(obs[:, 0], f32(g["obs"]).reshape(obs[:, 0].shape))
+    assert np.array_equal(rew[:, 0], f32(g["rew"]))
+    assert np.array_equal(done[:, 0].astype(bool), g["done"]) and np.array_equal(removed[:, 0], g["removed"])
+
+
+@needs_cxx
+@pytest.mark.parametrize("name", CL_WW)
+def test_emulated_waterworld_policy_reproduces_reference_closed_loop(name):
+    from emu.driver import EmuWaterworld
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    eng = EmuWaterworld(1, seed=int(g["seed"]), env_id_base=int(g["env_id"]), **json.loads(str(g["config"])))
+    check_closed_loop_golden_ww(g, eng.reset, lambda T, o: eng.rollout_heuristic(T, o, auto_reset=False), 1e-9)
+    assert eng.state(0)["counter"] == int(g["counter"])
+
+
+@needs_cxx
+@pytest.mark.parametrize("name", CL_PE)
+def test_emulated_pursuit_policy_reproduces_reference_closed_loop(name):
+    from emu.driver import EmuPursuit
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    maps = pool16() if str(g["maps"]) == "pool16" else small_map()
+    eng = EmuPursuit(1, maps, seed=int(g["seed"]), env_id_base=int(g["env_id"]), **json.loads(str(g["config"])))
+    check_closed_loop_golden_pe(g, eng.reset, lambda T, o: eng.rollout_heuristic(T, o, auto_reset=False,
+                                                                                py2_division=bool(g["py2"])))
+    assert eng.state(0)["counter"] == int(g["counter"])

@@ -8,7 +8,12 @@ import pytest
 import torch
 
 from oracle.heuristics_oracle import pursuit_action, waterworld_action
-from test_heuristics import (PE, WW, check_pursuit_closed_loop, check_waterworld_closed_loop, evader_window)
+import json
+import os
+
+from conftest import GOLDEN_DIR
+from test_heuristics import (CL_PE, CL_WW, PE, WW, check_closed_loop_golden_pe, check_closed_loop_golden_ww,
+                             check_pursuit_closed_loop, check_waterworld_closed_loop, pool16, small_map)
 
 pytestmark = pytest.mark.gpu
 
@@ -143,3 +148,38 @@ def test_generators_match_oracle():
             flat = np.concatenate([np.zeros((m, 2 * R * R), np.float32), conv[..., 2].reshape(m, -1), np.ones((m, 1), np.float32)], 1)
             got = pursuit_heuristic(torch.as_tensor(flat, device="cuda"), obs_range=R, py2_division=py2, fallback=torch.as_tensor(fb))
             assert list(n(got)) == want
+
+
+@pytest.mark.parametrize("name", CL_WW)
+def test_waterworld_policy_reproduces_reference_closed_loop(name):
+    """The REAL reference env stepped by the REAL reference policy (tests/golden/cl_ww_*.npz) vs the fp64 engine's
+    in-kernel policy rollout: actions, observations, rewards <= 1e-9, catches equal, over the whole trajectory."""
+    from madrl_b200 import BatchedMAWaterWorld
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    eng = BatchedMAWaterWorld(1, seed=int(g["seed"]), env_id_base=int(g["env_id"]), dtype=torch.float64,
+                              **json.loads(str(g["config"])))
+    last = {}
+
+    def reset():
+        last["o"] = eng.reset()
+        return n(last["o"])
+
+    check_closed_loop_golden_ww(g, reset, lambda T, o: [n(x) for x in eng.rollout_heuristic(T, last["o"], auto_reset=False)], 1e-9)
+    assert int(eng.state["rng_counter"][0]) == int(g["counter"])
+
+
+@pytest.mark.parametrize("name", CL_PE)
+def test_pursuit_policy_reproduces_reference_closed_loop(name):
+    from madrl_b200 import BatchedPursuitEvade
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    maps = pool16() if str(g["maps"]) == "pool16" else small_map()
+    eng = BatchedPursuitEvade(1, maps, seed=int(g["seed"]), env_id_base=int(g["env_id"]), **json.loads(str(g["config"])))
+    last = {}
+
+    def reset():
+        last["o"] = eng.reset()
+        return n(last["o"])
+
+    check_closed_loop_golden_pe(g, reset, lambda T, o: [n(x) for x in eng.rollout_heuristic(
+        T, last["o"], auto_reset=False, py2_division=bool(g["py2"]))])
+    assert int(eng.state["rng_counter"][0]) == int(g["counter"])
