@@ -175,7 +175,8 @@ class BatchedPursuitEvade(object):
                                                      _ptr(done), _ptr(info), int(auto_reset), self._stream()))
         return obs, rew, done, info
 
-    def rollout_heuristic(self, T, obs0, auto_reset=True, out=None, record_actions=True, py2_division=True):
+    def rollout_heuristic(self, T, obs0, auto_reset=True, out=None, record_actions=True, py2_division=True,
+                          actions_out=None):
         """T lockstep steps in one launch with the reference's hand-written policy
         (heuristics/pursuit.py:18-50: walk towards the nearest visible evader, a random move when none is
         visible) evaluated inside the kernel: closed loop, no action tensor, no per-step launch.
@@ -192,7 +193,10 @@ class BatchedPursuitEvade(object):
             info = torch.empty((T, E), dtype=torch.int32, device=self.device)
         else:
             obs, rew, done, info = self._require_outputs(T, out, self.device)
-        act = torch.empty((T, E, Np), dtype=torch.int32, device=self.device) if record_actions else None
+        if actions_out is not None:   # caller-owned buffer for the actions taken (no allocation in a rollout loop)
+            act = _lib.require_tensor(actions_out, "actions_out", torch.int32, (T, E, Np), self.device)
+        else:
+            act = torch.empty((T, E, Np), dtype=torch.int32, device=self.device) if record_actions else None
         with torch.cuda.device(self.device):
             _lib.check(self._L.madrl_pursuit_rollout_heuristic(
                 self._h, T, _ptr(obs0), _ptr(act), _ptr(obs), _ptr(rew), _ptr(done), _ptr(info), int(auto_reset),

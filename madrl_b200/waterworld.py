@@ -196,7 +196,7 @@ class BatchedMAWaterWorld(object):
                                                 _ptr(done), _ptr(info), int(auto_reset), self._stream()))
         return obs, rew, done, info
 
-    def rollout_heuristic(self, T, obs0, auto_reset=True, out=None, record_actions=True):
+    def rollout_heuristic(self, T, obs0, auto_reset=True, out=None, record_actions=True, actions_out=None):
         """T lockstep steps in one launch with the reference's hand-written policy
         (heuristics/waterworld.py:11-53) evaluated inside the kernel: closed loop, no action tensor,
         no per-step launch.  obs0 [E, Np, D] = the observation the first action is computed from
@@ -211,7 +211,10 @@ class BatchedMAWaterWorld(object):
             info = torch.empty((T, E, 2), dtype=torch.int32, device=self.device)
         else:
             obs, rew, done, info = self._require_outputs(T, out, self.device)
-        act = torch.empty((T, E, Np, 2), dtype=self.dtype, device=self.device) if record_actions else None
+        if actions_out is not None:   # caller-owned buffer for the actions taken (no allocation in a rollout loop)
+            act = _lib.require_tensor(actions_out, "actions_out", self.dtype, (T, E, Np, 2), self.device)
+        else:
+            act = torch.empty((T, E, Np, 2), dtype=self.dtype, device=self.device) if record_actions else None
         with torch.cuda.device(self.device):
             _lib.check(self._L.madrl_ww_rollout_heuristic(self._h, T, _ptr(obs0), _ptr(act), _ptr(obs), _ptr(rew),
                                                           _ptr(done), _ptr(info), int(auto_reset), self._stream()))
