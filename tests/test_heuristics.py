@@ -340,3 +340,63 @@ def test_emulated_pursuit_policy_reproduces_reference_closed_loop(name):
     check_closed_loop_golden_pe(g, eng.reset, lambda T, o: eng.rollout_heuristic(T, o, auto_reset=False,
                                                                                 py2_division=bool(g["py2"])))
     assert eng.state(0)["counter"] == int(g["counter"])
+
+
+# ------------------------------------------------------------------------------ random configurations
+@needs_cxx
+@pytest.mark.parametrize("case", range(6))
+def test_emulated_waterworld_policy_random_configurations(case):
+    """Every template shape of the POLICY instantiation (1-8 objects per lane, 1-2 sensors per lane, compile-time and
+    run-time K, global / local reward, random obstacle, horizon resets) closes the loop like the oracle does."""
+    from emu.driver import EmuWaterworld
+    rs = np.random.RandomState(1000 + case)
+    Np = int(rs.choice([1, 2, 3, 7, 12, 32]))
+    shape = [(3, 2), (20, 9), (60, 40), (120, 100), (4, 4), (1, 1)][case]
+    cfg = dict(n_pursuers=Np, n_evaders=int(shape[0]), n_poison=int(shape[1]), n_sensors=int(rs.choice([1, 5, 30, 33, 64])),
+               n_coop=int(rs.choice([1, 2])), radius=float(rs.choice([0.015, 0.04])), sensor_range=float(rs.choice([0.2, 0.35])),
+               reward_mech=str(rs.choice(['local', 'global'])), addid=bool(rs.randint(2)),
+               obstacle_loc=None if rs.randint(2) else np.array([0.5, 0.5]))
+    if Np + shape[0] + shape[1] > 256:
+        cfg['n_pursuers'] = Np = 8
+    E, T, seed, base, mpl = 2, 7, 77 + case, 10 * case, 5
+    eng = EmuWaterworld(E, seed=seed, env_id_base=base, max_path_length=mpl, **cfg)
+    obs0 = eng.reset()
+    act, obs, rew, done, info = eng.rollout_heuristic(T, obs0, auto_reset=True)
+    # a sum that cancels to rounding noise is normalised to a noise-determined direction (see DESIGN.md section 5):
+    # such decisions (norm < 1e-9) are not comparable, everything downstream of one is skipped
+    for e in range(E):
+        o = WaterworldOracle(rng=Stream(seed, base + e), **cfg)
+        o.reset()
+        prev, ts = obs0[e].astype(np.float64), 0
+        for t in range(T):
+            norms = [waterworld_action(prev[i], return_norm=True) for i in range(Np)]
+            if any(0 < n_ < 1e-9 for _, n_ in norms):
+                break
+            for i, (want, _) in enumerate(norms):
+                assert np.abs(want - act[t, e, i]).max() < 1e-9, (t, e, i)
+            oo, rr, dd, ii = o.step(act[t, e].astype(np.float64))
+            ts += 1
+            dd = dd or ts >= mpl
+            assert bool(done[t, e]) == dd and [ii['evcatches'], ii['pocatches']] == list(info[t, e])
+            if dd:
+                oo, ts = o.reset(), 0
+            assert np.abs(np.array(oo) - obs[t, e]).max() < 1e-9 and np.abs(rr - rew[t, e]).max() < 1e-9
+            prev = obs[t, e].astype(np.float64)
+
+
+@needs_cxx
+@pytest.mark.parametrize("case", range(5))
+def test_emulated_pursuit_policy_random_configurations(case):
+    from emu.driver import EmuPursuit
+    rs = np.random.RandomState(2000 + case)
+    R = int(rs.choice([1, 2, 3, 6, 11]))
+    cfg = dict(n_evaders=int(rs.choice([1, 5, 33, 64])), n_pursuers=int(rs.choice([1, 4, 9, 32])), obs_range=R,
+               surround=bool(rs.randint(2)), n_catch=int(rs.choice([1, 2])), flatten=bool(rs.randint(2)),
+               reward_mech=str(rs.choice(['local', 'global'])), catchr=0.1, sample_maps=True, include_id=bool(rs.randint(2)))
+    maps = pool16() if case % 2 == 0 else small_map()
+    E, T, seed, base, mpl = 2, 12, 55 + case, 7 * case, 5
+    py2 = bool(case % 2)
+    eng = EmuPursuit(E, maps, seed=seed, env_id_base=base, max_path_length=mpl, **cfg)
+    obs0 = eng.reset()
+    act, obs, rew, done, removed = eng.rollout_heuristic(T, obs0, auto_reset=True, py2_division=py2)
+    check_pursuit_closed_loop(maps, cfg, seed, base, obs0, act, obs, rew, done, removed, mpl, py2)
