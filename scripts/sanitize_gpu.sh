@@ -23,6 +23,16 @@ pe = BatchedPursuitEvade(64, maps, n_evaders=30, n_pursuers=8, obs_range=7, samp
 pe.reset(); pe.rollout(torch.randint(0, 5, (12, 64, 8), dtype=torch.int32, device='cuda'))
 hw = BatchedHostageWorld(64, 10, 16, 16, 4, 2, seed=1, max_path_length=4); hw.reset()
 hw.rollout(torch.randn(9, 64, 10, 2, device='cuda'))
+# closed-loop (POLICY) instantiations, the stand-alone generators, path packing
+o = ww.reset(); ww.rollout_heuristic(6, o)
+o = c4.reset(); c4.rollout_heuristic(3, o)
+o = pe.reset(); pe.rollout_heuristic(12, o); pe.rollout_heuristic(5, o, py2_division=False)
+from madrl_b200.heuristics import waterworld_heuristic, pursuit_heuristic
+waterworld_heuristic(ww.reset(), 30); pursuit_heuristic(pe.reset(), obs_range=7)
+from madrl_b200.postproc import pack_paths
+a = torch.randn(6, 64, 5, 2, device='cuda') * 0.5
+ob, rw, dn, inf = ww.rollout(a)
+pack_paths(ob, a, rw, dn)
 torch.cuda.synchronize(); print("driver done")
 PY
 for tool in memcheck racecheck synccheck; do
