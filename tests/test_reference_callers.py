@@ -225,3 +225,48 @@ def test_vec_env_executor_hook_equals_reference_vec_env_executor(world, family):
         assert sorted(i1) == sorted(i2) and all(np.array_equal(i1[k], i2[k]) for k in i1), t
         resets += int(np.sum(d1))
     assert resets >= 2 * n
+
+
+# ------------------------------------------------------------------------------------ heuristic policies
+def test_reference_policies_drive_the_dropin_envs(world):
+    """The reference's hand-written policy OBJECTS (heuristics/waterworld.py, heuristics/pursuit.py) stepping the
+    drop-in env classes, per agent as the reference's Visualizer does, reproduce the closed-loop goldens that the same
+    policies produced on the reference envs (tests/golden/cl_*.npz)."""
+    import json
+    import os
+    from conftest import GOLDEN_DIR, ROOT
+    from oracle.heuristics_oracle import policy_draw
+    from oracle.refshim import load_reference_heuristics
+    WPol, PPol, _ = load_reference_heuristics()
+    OurWW, OurPE, _ = world["ours"]
+    g = np.load(os.path.join(GOLDEN_DIR, "cl_ww_c2.npz"))
+    env = OurWW(seed=int(g["seed"]), env_id=int(g["env_id"]), dtype=torch.float64, **json.loads(str(g["config"])))
+    pol = WPol(env.agents[0].observation_space, env.agents[0].action_space)
+    o = env.reset()
+    assert np.abs(np.array(o) - g["obs0"]).max() < 1e-9
+    for t in range(60):
+        a = np.array([pol.sample_actions(np.asarray(oi)[None])[0][0] for oi in o])
+        assert np.abs(a - g["actions"][t]).max() < 1e-9, t
+        o, r, d, i = env.step(a)
+        assert np.abs(np.array(o) - g["obs"][t]).max() < 1e-9 and np.abs(r - g["rew"][t]).max() < 1e-9
+        assert [i['evcatches'], i['pocatches']] == list(g["info"][t])
+    # Pursuit (heuristics/pursuit.py as it runs under this interpreter: Python 3 division)
+    g = np.load(os.path.join(GOLDEN_DIR, "cl_pe_conv_py3.npz"))
+    maps = np.load(os.path.join(ROOT, "maps", "map_pool16.npy"))
+    seed, env_id = int(g["seed"]), int(g["env_id"])
+    env = OurPE(maps, seed=seed, env_id=env_id, **json.loads(str(g["config"])))
+
+    class Space(object):
+        def sample(self):
+            raise AssertionError("every pursuer of this golden sees an evader")
+
+    pol = PPol(None, Space())
+    o = env.reset()
+    assert np.array_equal(np.array(o, dtype=np.float32), np.asarray(g["obs0"], dtype=np.float32))
+    for t in range(40):
+        a = [int(pol.sample_actions(np.asarray(oq))[0]) for oq in o]
+        assert a == list(g["actions"][t]), t
+        o, r, d, i = env.step(a)
+        assert np.array_equal(np.array(o, dtype=np.float32), np.asarray(g["obs"][t], dtype=np.float32))
+        assert i['removed'] == g["removed"][t] and d == bool(g["done"][t])
+    assert policy_draw(seed, env_id, 0, 0) in range(5)
