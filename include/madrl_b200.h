@@ -204,7 +204,10 @@ typedef struct madrl_pursuit_layout {
   size_t rng_counter;  /* uint64 [E]                                                              */
   size_t stale;        /* uint16 [E][Np][R*R]  the never-cleared channels 1-2 of local_obs
                           (pursuit_evade.py:119,438): pursuer count | evader count << 8           */
-  size_t maps;         /* uint8  [n_maps][xs*ys] 1 = building (constant)                          */
+  size_t maps;         /* uint32 [n_maps][(xs+2p)(ys+2p)], p = (obs_range-1)/2+1: per map the empty cell grid
+                          with its border of p marker cells, as the kernel keeps it in shared memory:
+                          bit 0 building, bits 24-26 need_to_surround (pursuit_evade.py:523-540), border
+                          cells 0x80000001 (constant)                                             */
   size_t lut, idv;     /* float tables (constant)                                                 */
   int32_t n_agents, obs_dim;
 } madrl_pursuit_layout;

@@ -44,7 +44,7 @@ struct PEParams {
   double constraint_window, catchr, term_pursuit, urgency;
   float wall_val, one_val;        // float32(1/layer_norm) the two ways the reference gets it
   uint64_t seed;
-  const uint8_t* maps;            // [n_maps][xs*ys] 1 = building
+  const uint32_t* maps;           // [n_maps][ncellP] the empty bordered cell grid of each map, as the kernel keeps it in shared memory
   const float* lut;               // [256] float32(count)/float32(layer_norm)
   const float* idv;               // [Np]  float32(float64(i)/Np)
   // state records
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
   const int lane = threadIdx.x, wib = 0;
   const int warp_global = blockIdx.x;
   const int warp_stride = gridDim.x;
-  const int R = RC > 0 ? RC : p.R, RR = R * R, xs = p.xs, ys = p.ys, ncell = xs * ys;
+  const int R = RC > 0 ? RC : p.R, RR = R * R, xs = p.xs, ys = p.ys;
   const int Np = p.Np, Ne = p.Ne, Nag = Np + Ne;
 
   // shared memory: block-wide count->value table, then per warp: cell words, stale window counts
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
   // map cell (x, y) lives at cell0 + 4 (x ysP + y): a border of `pad` marker cells surrounds the map
   const int ysP = p.ysP;
   const uint32_t cell0 = cell_a + 4u * (uint32_t)(p.pad * ysP + p.pad);
-  constexpr uint32_t BORDER = 0x80000001u;   // bit 31 = outside the map; byte 0 = 1: nobody moves there
+  // border cells hold 0x80000001: bit 31 = outside the map; byte 0 = 1: nobody moves there (no bounds tests in the moves)
   const float my_idv = (lane < p.Np) ? p.idv[lane] : 0.0f;   // lane i keeps float32(i / Np)
 
   // per-lane window cells: local_obs[i, ch, wx, wy] <-> map cell (x - off + wx, y - off + wy) (pe:430-438), as a byte
@@ -165,10 +165,10 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
     }
     int map_id = p.map_id[e], ts = p.path_len[e];
     uint64_t ctr = p.ctr[e];
-    const uint8_t* map = p.maps + (size_t)map_id * ncell;
+    const uint32_t* map = p.maps + (size_t)map_id * p.ncellP + (p.pad * ysP + p.pad);   // cell (x, y) at map[x ysP + y]
     for (int i = lane; i < Np * RR; i += 32) sts_u16(stale_a + 2u * i, p.stale[(size_t)e * Np * RR + i]);
     bool rebuild = true;   // cell words must be (re)built from map + positions
-    uint64_t cblk = ~0ull;   // first cached Philox block (warp-uniform); ~0 = cache empty
+    int coff = -1;   // word offset of draw `ctr` inside the warp's cache of 32 Philox blocks (warp-uniform); < 0 = cache empty
 
     float* obs_t = p.obs + (size_t)e * Np * p.D;
     float* rew_t = p.rew + (size_t)e * Np + lane;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
           // never exist (not spawned, no draws, not live)
           const int n_ev = p.max_opponents > 0 ? rs.next_range(1, p.max_opponents) : Ne;
           if (p.sample_maps) map_id = rs.next_range(0, p.n_maps);                    // pe:183
-          map = p.maps + (size_t)map_id * ncell;
+          map = p.maps + (size_t)map_id * p.ncellP + (p.pad * ysP + p.pad);
           const double span = 1.0 - p.constraint_window;
           const double xws = 0.0 + (span - 0.0) * rs.next_unit<double>();             // pe:185
           const double yws = 0.0 + (span - 0.0) * rs.next_unit<double>();             // pe:186
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
             do {
               x = rs.next_range(xl, xu);
               y = rs.next_range(yl, yu);
-            } while (map[x * ys + y] != 0);
+            } while ((map[x * ysP + y] & 1u) != 0u);
             if (a < Np) { if (lane == a) { px = x; py = y; } }
             else {
               const int j = a - Np;
@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
             }
           }
           ctr = rs.counter;
+          coff = -1;   // the reset consumed draws: the cached words no longer start at `ctr`
           ts = 0;
 #pragma unroll
           for (int c = 0; c < EPL; ++c) live[c] = __ballot_sync(FULL_MASK, lane + 32 * c < n_ev);
@@ -251,10 +252,11 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
         }
         if (rebuild) {   // cell words from scratch: building flag + occupancy counts
           __syncwarp();
-          for (int i = lane; i < p.ncellP; i += 32) {
-            const int X = i / ysP, x = X - p.pad, y = i - X * ysP - p.pad;
-            const bool in = (unsigned)x < (unsigned)xs && (unsigned)y < (unsigned)ys;
-            sts_u32(cell_a + 4u * i, in ? (map[x * ys + y] ? 1u : 0u) : BORDER);
+          // the empty grid of this map (building flags, need_to_surround bits, border markers) is a table the host
+          // laid out exactly like the shared-memory grid: the rebuild is a straight copy
+          {
+            const uint32_t* grid = map - (p.pad * ysP + p.pad);
+            for (int i = lane; i < p.ncellP; i += 32) sts_u32(cell_a + 4u * i, __ldg(grid + i));
           }
           __syncwarp();
           if (lane < Np) reds_add_u32(cell0 + 4u * (px * ysP + py), 1u << 8);
@@ -281,8 +283,8 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
             const int dx = (a == 0) ? -1 : (a == 1 ? 1 : 0), dy = (a == 2) ? 1 : (a == 3 ? -1 : 0);
             const int nx = px + dx, ny = py + dy;
             const uint32_t cur = cell0 + 4u * (px * ysP + py), nxt = cell0 + 4u * (nx * ysP + ny);
-            if ((unsigned)a < 4u && (unsigned)nx < (unsigned)xs && (unsigned)ny < (unsigned)ys &&
-                lds_low_byte(cur) == 0u && lds_low_byte(nxt) == 0u) {
+            // da:69-97: no move out of bounds or into a building -- both are "byte 0 set" in the bordered grid
+            if ((unsigned)a < 4u && lds_low_byte(cur) == 0u && lds_low_byte(nxt) == 0u) {
               reds_add_u32(cur, 0u - (1u << 8));
               reds_add_u32(nxt, 1u << 8);
               px = nx; py = ny;
@@ -294,11 +296,11 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
             int n_draws = 0;
 #pragma unroll
             for (int c = 0; c < EPL; ++c) n_draws += __popc(live[c]);
-            // words [ctr, ctr + n_draws) must lie in blocks [cblk, cblk + 32)
-            if (cblk == ~0ull || (ctr >> 2) < cblk || ((ctr + (uint64_t)n_draws + 3u) >> 2) > cblk + 32u) {
+            // words [ctr, ctr + n_draws) must lie in the 128 cached words
+            if (coff < 0 || coff + n_draws > 128) {
               __syncwarp();   // every lane's reads of the previous fill precede the overwrite
-              cblk = ctr >> 2;
-              const uint64_t b = cblk + (uint64_t)lane;
+              coff = (int)(ctr & 3u);
+              const uint64_t b = (ctr >> 2) + (uint64_t)lane;
               const Philox4 blk = philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), env_id, 0u, (uint32_t)p.seed,
                                                 (uint32_t)(p.seed >> 32));
 #pragma unroll
@@ -311,13 +313,12 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
             const bool alive = (live[c] >> lane) & 1u;
             const int rank = base_rank + __popc(live[c] & lanemask_lt());
             if (alive) {
-              const uint32_t word = lds_u32(wcache_a + 4u * (uint32_t)(ctr + (uint64_t)rank - 4u * cblk));
+              const uint32_t word = lds_u32(wcache_a + 4u * (uint32_t)(coff + rank));
               const int a = u32_to_range(word, 0, 5);
               const int dx = (a == 0) ? -1 : (a == 1 ? 1 : 0), dy = (a == 2) ? 1 : (a == 3 ? -1 : 0);
               const int nx = ex[c] + dx, ny = ey[c] + dy;
               const uint32_t cur = cell0 + 4u * (ex[c] * ysP + ey[c]), nxt = cell0 + 4u * (nx * ysP + ny);
-              if (a < 4 && (unsigned)nx < (unsigned)xs && (unsigned)ny < (unsigned)ys &&
-                  lds_low_byte(cur) == 0u && lds_low_byte(nxt) == 0u) {
+              if (a < 4 && lds_low_byte(cur) == 0u && lds_low_byte(nxt) == 0u) {
                 reds_add_u32(cur, 0u - (1u << 16));
                 reds_add_u32(nxt, 1u << 16);
                 ex[c] = nx; ey[c] = ny;
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
             base_rank += __popc(live[c]);
           }
           ctr += (uint64_t)base_rank;
+          coff += base_rank;
           __syncwarp();
           // ---- remove_agents: pe:463-521 -----------------------------------------------------------
 #pragma unroll
@@ -334,20 +336,16 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
             if ((live[c] >> lane) & 1u) {
               const int x = ex[c], y = ey[c];
               if (p.surround) {
-                // neighbours holding >= 1 pursuer (pe:482-485) vs need_to_surround (pe:523-540)
-                int adj = 0, need = 4;
-                if (x == 0 || x == xs - 1) need -= 1;
-                if (y == 0 || y == ys - 1) need -= 1;
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                  const int xn = x + (m == 0 ? -1 : (m == 1 ? 1 : 0)), yn = y + (m == 2 ? 1 : (m == 3 ? -1 : 0));
-                  if ((unsigned)xn < (unsigned)xs && (unsigned)yn < (unsigned)ys) {
-                    const uint32_t wv = lds_u32(cell0 + 4u * (xn * ysP + yn));
-                    if ((wv >> 8) & 0xff) adj += 1;
-                    // pe:536 skips neighbours with xn <= 0 or yn <= 0: row/column 0 never subtracts
-                    if (xn > 0 && yn > 0 && (wv & 0xff)) need -= 1;
-                  }
-                }
+                // neighbours holding >= 1 pursuer (pe:482-485) vs need_to_surround (pe:523-540).  need_to_surround
+                // depends on the map only (borders, buildings next to the cell, the row/column-0 quirk of pe:536): the
+                // host tabulates it per cell (pe_need_to_surround) and the rebuild keeps it in bits 24-26 of the cell
+                // word; border cells hold no pursuers, so the four neighbour loads need no bounds tests
+                const uint32_t own = cell0 + 4u * (uint32_t)(x * ysP + y);
+                const int need = (int)((lds_u32(own) >> 24) & 7u);
+                const int adj = (int)(((lds_u32(own - 4u * (uint32_t)ysP) >> 8) & 0xffu) != 0u) +
+                                (int)(((lds_u32(own + 4u * (uint32_t)ysP) >> 8) & 0xffu) != 0u) +
+                                (int)(((lds_u32(own + 4u) >> 8) & 0xffu) != 0u) +
+                                (int)(((lds_u32(own - 4u) >> 8) & 0xffu) != 0u);
                 got = (adj == need);
               } else {
                 got = (int)((lds_u32(cell0 + 4u * (x * ysP + y)) >> 8) & 0xff) >= p.n_catch;   // pe:498
@@ -542,7 +540,10 @@ extern "C" int madrl_pursuit_state_layout(const madrl_pursuit_config* c, madrl_p
   out->map_id = take(4 * E);
   out->path_len = take(4 * E);
   out->stale = take(2 * (size_t)c->n_pursuers * RR * E);
-  out->maps = take((size_t)c->n_maps * c->xs * c->ys);
+  {
+    const size_t pad = (size_t)(c->obs_range - 1) / 2 + 1;
+    out->maps = take(4 * (size_t)c->n_maps * (c->xs + 2 * pad) * (c->ys + 2 * pad));
+  }
   out->lut = take(4 * 256);
   out->idv = take(4 * 32);
 
@@ -576,15 +577,40 @@ extern "C" int madrl_pursuit_create(const madrl_pursuit_config* c, const int32_t
   e = cudaMemset(h->state, 0, lay.total_bytes);   // agents start at (0,0), local_obs zeroed (pe:119, au:22)
   if (e != cudaSuccess) { set_error("cudaMemset: %s", cudaGetErrorString(e)); madrl_pursuit_destroy(h); return MADRL_ECUDA; }
   // constant tables
+  // constant table: per map the EMPTY bordered cell grid exactly as the kernel keeps it in shared memory (a rebuild
+  // is a straight copy).  Word of map cell (x, y) at [(x + pad) ysP + (y + pad)]:
+  //   bit 0      building (da:110-113)
+  //   bits 24-26 need_to_surround of the cell (pe:523-540), static per map:
+  //              4 - [x on an x-border] - [y on a y-border] - #{in-bounds neighbours with xn > 0 and yn > 0 that are
+  //              buildings} (pe:536 skips neighbours with xn <= 0 or yn <= 0: a building in row / column 0 never subtracts)
+  //   border cells (a frame of `pad` cells): 0x80000001 = outside the map + nobody moves there
   const size_t ncell = (size_t)c->xs * c->ys, nm = (size_t)c->n_maps;
-  uint8_t* m8 = new (std::nothrow) uint8_t[nm * ncell];
+  const int pad = (c->obs_range - 1) / 2 + 1, ysP = c->ys + 2 * pad, xsP = c->xs + 2 * pad;
+  const size_t ncellP = (size_t)xsP * ysP;
+  uint32_t* m8 = new (std::nothrow) uint32_t[nm * ncellP];
   if (!m8) { madrl_pursuit_destroy(h); return MADRL_ENOMEM; }
-  for (size_t i = 0; i < nm * ncell; ++i) m8[i] = (map_pool_host[i] == -1) ? 1 : 0;   // da:110-113
+  for (size_t mi = 0; mi < nm; ++mi) {
+    const int32_t* mp = map_pool_host + mi * ncell;
+    uint32_t* g = m8 + mi * ncellP;
+    for (size_t i = 0; i < ncellP; ++i) g[i] = 0x80000001u;
+    for (int x = 0; x < c->xs; ++x)
+      for (int y = 0; y < c->ys; ++y) {
+        int need = 4;
+        if (x == 0 || x == c->xs - 1) need -= 1;
+        if (y == 0 || y == c->ys - 1) need -= 1;
+        const int dxs[4] = {-1, 1, 0, 0}, dys[4] = {0, 0, 1, -1};                       // pe:150 surround_mask
+        for (int m = 0; m < 4; ++m) {
+          const int xn = x + dxs[m], yn = y + dys[m];
+          if (xn > 0 && yn > 0 && xn < c->xs && yn < c->ys && mp[xn * c->ys + yn] == -1) need -= 1;
+        }
+        g[(size_t)(x + pad) * ysP + (y + pad)] = (mp[x * c->ys + y] == -1 ? 1u : 0u) | ((uint32_t)(need < 0 ? 0 : need) << 24);
+      }
+  }
   float lut[256], idv[32];
   const float lnf = (float)c->layer_norm;
   for (int k = 0; k < 256; ++k) lut[k] = (float)k / lnf;            // float32 |count| / layer_norm (pe:438)
   for (int i = 0; i < 32; ++i) idv[i] = (float)((double)i / (double)c->n_pursuers);   // pe:445
-  e = cudaMemcpy(h->state + lay.maps, m8, nm * ncell, cudaMemcpyHostToDevice);
+  e = cudaMemcpy(h->state + lay.maps, m8, 4 * nm * ncellP, cudaMemcpyHostToDevice);
   delete[] m8;
   if (e == cudaSuccess) e = cudaMemcpy(h->state + lay.lut, lut, sizeof(lut), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->state + lay.idv, idv, sizeof(idv), cudaMemcpyHostToDevice);
@@ -709,7 +735,7 @@ static int pe_launch(madrl_pursuit* h, int mode, int T, const int32_t* actions, 
   p.one_val = 1.0f / (float)c.layer_norm;             // float32 |+-1| / layer_norm
   p.seed = c.seed;
   char* st = h->state;
-  p.maps = (const uint8_t*)(st + h->lay.maps); p.lut = (const float*)(st + h->lay.lut);
+  p.maps = (const uint32_t*)(st + h->lay.maps); p.lut = (const float*)(st + h->lay.lut);
   p.idv = (const float*)(st + h->lay.idv);
   p.pos = (uint8_t*)(st + h->lay.pos); p.gone = (uint64_t*)(st + h->lay.gone);
   p.map_id = (int32_t*)(st + h->lay.map_id); p.path_len = (int32_t*)(st + h->lay.path_len);
