@@ -81,7 +81,9 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
   for (int c = 0; c < OPL; ++c) {
     const int o = obase + lane + 32 * c;
     const bool isC = o >= cLo && o < hLo, isH = o >= hLo && o < Nall;
-    cull2_l[c] = (isC || isH) ? p.cull2 : (real)-1;      // allies are sensed but never emitted (hw:395-397)
+    cull2_l[c] = p.cull2;   // uniform: lanes beyond the last object hold a far-away sentinel position instead of a
+                            // per-lane validity select (allies are sensed but never emitted, hw:395-397: they
+                            // are not among the chunk objects)
     coll2_l[c] = isC ? p.coll2_c : (isH ? p.coll2_h : (real)-1);
     mC[c] = __ballot_sync(FULL_MASK, isC);
     mH[c] = __ballot_sync(FULL_MASK, isH);
@@ -106,8 +108,8 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
     for (int c = 0; c < OPL; ++c) {
       const int o = obase + lane + 32 * c;
       const bool v = o < Nall;
-      x[c] = v ? rec[o] : (real)0;
-      y[c] = v ? rec[Nall + o] : (real)0;
+      x[c] = v ? rec[o] : (real)1e18;            // sentinel: never in range of anything, never written back
+      y[c] = v ? rec[Nall + o] : (real)1e18;
       vx[c] = v ? rec[2 * Nall + o] : (real)0;
       vy[c] = v ? rec[3 * Nall + o] : (real)0;
       col[c] = 0u;
@@ -166,13 +168,7 @@ hw_kernel(const __grid_constant__ HWParams<real> p) {
           for (int c = 0; c < OPL; ++c) {
             const int o = obase + lane + 32 * c;
             sav[c] = false;
-            if (!1 && o < cLo) {                                // hw:155-159
-              const uint64_t b = n + 2 * (uint64_t)o;
-              x[c] = unit_at<real>(p.seed, env_id, b);
-              const real yy = unit_at<real>(p.seed, env_id, b + 1);
-              y[c] = yy < (real)0.55 ? (real)0.55 : (yy > (real)0.95 ? (real)0.95 : yy);
-              vx[c] = 0; vy[c] = 0;
-            } else if (o < hLo) {                                            // hw:171-174
+            if (o < hLo) {                                                   // hw:171-174 (o >= cLo: rescuers are not chunk objects)
               const uint64_t b = n + 2 * (uint64_t)p.Nr + 3 * (uint64_t)p.Nh + 4 * (uint64_t)(o - cLo);
               x[c] = unit_at<real>(p.seed, env_id, b);
               y[c] = unit_at<real>(p.seed, env_id, b + 1);
