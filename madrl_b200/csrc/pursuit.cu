@@ -100,7 +100,9 @@ __device__ __forceinline__ double numpy_mean(const double* a, int n) {
 // RC = compile-time obs_range (0 = runtime p.R).
 // POLICY = the pursuers' actions come from the in-kernel heuristic policy instead of the action tensor
 // (a separate instantiation: the open-loop kernel carries none of its instructions).
-template <int EPL, int CPL, int RC, bool POLICY = false>
+// FLAT = flatten=True layout (3R^2 [+1]); false = the (R, R, 4) conv layout: compile-time, so the window loop has no
+// layout branch.
+template <int EPL, int CPL, int RC, bool POLICY, bool FLAT>
 __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEParams p) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   const int lane = threadIdx.x, wib = 0;
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
 #pragma unroll
         for (int it = 0; it < CPL; ++it) {
           const int w = lane + 32 * it;
-          if (w < RR && (p.flatten ? o0[2 * RR + w] : o0[4 * w + 2]) > 0.0f) key = min(key, pkey[it]);
+          if (w < RR && (FLAT ? o0[2 * RR + w] : o0[4 * w + 2]) > 0.0f) key = min(key, pkey[it]);
         }
         key = __reduce_min_sync(FULL_MASK, key);
         if (lane == i)
@@ -385,10 +387,11 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
             float v1[CPL], v2[CPL];
 #pragma unroll
             for (int it = 0; it < CPL; ++it) {
-              if (inb[it]) c12[it] = (wv[it] >> 8) & 0xffffu;
+              if (inb[it]) c12[it] = __byte_perm(wv[it], 0u, 0x4421u);   // (wv >> 8) & 0xffff: pursuer | evader << 8
               if (lane + 32 * it < RR) sts_u16(st_row + 64u * it, c12[it]);
-              v1[it] = lds_f32(lut_a + 4u * (c12[it] & 0xffu));         // float32(k) / float32(layer_norm)
-              v2[it] = lds_f32(lut_a + 4u * (c12[it] >> 8));
+              // byte extraction as PRMT so that the table address is one LEA (was shift + mask + add per lookup)
+              v1[it] = lds_f32(lut_a + 4u * __byte_perm(c12[it], 0u, 0x4440u));   // float32(k) / float32(layer_norm)
+              v2[it] = lds_f32(lut_a + 4u * __byte_perm(c12[it], 0u, 0x4441u));
             }
             if constexpr (POLICY) {   // heuristics/pursuit.py:18-50 on the evader channel just assembled
               uint32_t key = 0xffffffffu;
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
                 next_act = key != 0xffffffffu ? (int)p.policy_lut[key & 0xffu]
                                               : u32_to_range(stream_word(p.seed, env_id, PE_POLICY_TAG, ctr * 32u + (uint64_t)i), 0, 5);
             }
-            if (p.flatten) {
+            if constexpr (FLAT) {
 #pragma unroll
               for (int it = 0; it < CPL; ++it) {
                 const int w = lane + 32 * it;
@@ -426,7 +429,7 @@ __global__ void __launch_bounds__(32, 28) pe_kernel(const __grid_constant__ PEPa
               }
             }
           }
-          if (p.flatten && n_tail && lane < Np) store_stream(obs_t + (size_t)lane * p.D + 3 * RR, my_idv);   // pe:444-445
+          if (FLAT && n_tail && lane < Np) store_stream(obs_t + (size_t)lane * p.D + 3 * RR, my_idv);   // pe:444-445
         }
         need_reset = false;
         if (!pass) {
@@ -682,10 +685,10 @@ void pe_policy_table(int R, int c2, uint8_t* lut) {
   }
 }
 
-template <int EPL, int CPL, int RC, bool POLICY>
-static int pe_launch_inst2(madrl_pursuit* h, PEParams& p, cudaStream_t stream) {
+template <int EPL, int CPL, int RC, bool POLICY, bool FLAT>
+static int pe_launch_inst3(madrl_pursuit* h, PEParams& p, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)p.smem_per_warp;   // block LUT + per-warp regions
-  const auto kfn = pe_kernel<EPL, CPL, RC, POLICY>;
+  const auto kfn = pe_kernel<EPL, CPL, RC, POLICY, FLAT>;
   MADRL_REQUIRE(smem <= 200 * 1024, "map too large for shared memory (%zu B per block)", smem);
   if (smem > 48 * 1024)
     MADRL_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -699,6 +702,12 @@ static int pe_launch_inst2(madrl_pursuit* h, PEParams& p, cudaStream_t stream) {
   g_launches.fetch_add(1);
   MADRL_CUDA_CHECK(cudaGetLastError());
   return MADRL_OK;
+}
+
+template <int EPL, int CPL, int RC, bool POLICY>
+static int pe_launch_inst2(madrl_pursuit* h, PEParams& p, cudaStream_t stream) {
+  return p.flatten ? pe_launch_inst3<EPL, CPL, RC, POLICY, true>(h, p, stream)
+                   : pe_launch_inst3<EPL, CPL, RC, POLICY, false>(h, p, stream);
 }
 
 template <int EPL, int CPL, int RC>

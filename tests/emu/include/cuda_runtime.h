@@ -173,6 +173,12 @@ static inline float fminf_(float a, float b) { return a < b ? a : b; }
 
 // ---- scalar intrinsics ---------------------------------------------------------------------------
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {   // PRMT, default mode
+  const uint64_t src = ((uint64_t)y << 32) | x;
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) r |= (unsigned)((src >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
+  return r;
+}
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline unsigned __float_as_uint(float v) { return (unsigned)madrl_emu::to_bits(v); }
 static inline float __int_as_float(int v) { return madrl_emu::from_bits<float>((uint32_t)v); }
