@@ -168,7 +168,10 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
     sx_l[kc] = (k < K) ? p.sensors[k] : (real)0;
     sy_l[kc] = (k < K) ? p.sensors[K + k] : (real)0;
   }
-  const int n_feat = p.speed_features ? 7 : 4;
+  // the compile-time-K instantiation is also the speed_features = True one (the reference's defaults: K = 30, 7 rows
+  // per sensor): no layout branch per pursuer; every other combination takes the KC = 0 instantiation
+  const bool speed = KC > 0 ? true : (p.speed_features != 0);
+  const int n_feat = speed ? 7 : 4;
   typedef typename Vec2<real>::type V2;
 
   for (int e = warp_global; e < p.E; e += warp_stride) {
@@ -385,7 +388,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
                   pwx += w * sx; pwy += w * sy;
                 }
               }
-              if (p.speed_features) {
+              if (speed) {
                 // slot 0 is read when nothing was sensed; its (possibly stale) value is masked below
                 real oEx, oEy, oPx, oPy, oUx, oUy;
                 CandSlot<real>::vel(aE[kc], oEx, oEy);
@@ -453,7 +456,7 @@ ww_kernel(const __grid_constant__ WWParams<real> p) {
                 pwx += w * sx; pwy += w * sy;
               }
             }
-            if (p.speed_features) {
+            if (speed) {
               real oEx, oEy, oPx, oPy, oUx, oUy;
               if (OPL == 1) {
                 oEx = __shfl_sync(FULL_MASK, vx[0], iE[kc]); oEy = __shfl_sync(FULL_MASK, vy[0], iE[kc]);
@@ -870,7 +873,7 @@ static int ww_launch(madrl_ww* h, int mode, int T, const void* actions, void* ob
 
   const int opl = (p.Nall + 31) / 32, kch = (p.K + 31) / 32;
 #define MADRL_WW_CASE(O, KH, KC_) return ww_launch_inst<real, O, KH, KC_>(h, p, stream)
-  if (p.K == 30) {   // the reference's n_sensors default: compile-time K
+  if (p.K == 30 && p.speed_features) {   // the reference's defaults (n_sensors = 30, speed features): compile-time K and layout
     if (opl == 1) MADRL_WW_CASE(1, 1, 30);
     if (opl == 2) MADRL_WW_CASE(2, 1, 30);
     if (opl <= 4) MADRL_WW_CASE(4, 1, 30);

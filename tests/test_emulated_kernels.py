@@ -50,13 +50,15 @@ WW = {
     "k40": dict(n_pursuers=4, n_evaders=40, n_poison=3, n_sensors=40, n_coop=2, radius=0.03),  # 2 sensors per lane
     "big200": dict(n_pursuers=6, n_evaders=120, n_poison=74, n_coop=2, radius=0.02),          # 8 objects per lane
     "minimum": dict(n_pursuers=1, n_evaders=1, n_poison=1, n_sensors=1, n_coop=1, radius=0.05),
+    # K = 30 WITHOUT speed features: must not take the compile-time (K = 30, speed features) instantiation
+    "k30_nospeed": dict(n_pursuers=3, n_evaders=4, n_poison=5, n_sensors=30, speed_features=False, radius=0.03),
     "np32_k64": dict(n_pursuers=32, n_evaders=3, n_poison=2, n_sensors=64, n_coop=3, radius=0.03),
 }
 
 
 @pytest.mark.parametrize("variant", sorted(VARIANTS))
 @pytest.mark.parametrize("name,E,T", [("c2", 5, 60), ("dense", 5, 80), ("global_nospeed_randobst", 5, 80),
-                                      ("c4", 3, 8), ("k40", 3, 25), ("big200", 2, 6), ("minimum", 5, 60),
+                                      ("c4", 3, 8), ("k40", 3, 25), ("big200", 2, 6), ("minimum", 5, 60), ("k30_nospeed", 3, 40),
                                       ("np32_k64", 2, 6)])
 def test_waterworld_fp64_trajectories_match_oracle(variant, name, E, T):
     from emu.driver import EmuWaterworld
