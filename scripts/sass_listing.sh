@@ -11,5 +11,5 @@ dump() {  # out, object, mangled name
 }
 dump ww_c2 $B/waterworld.o _ZN5madrl9ww_kernelIfLi1ELi1ELi30ELb0ELb0EEEvNS_8WWParamsIT_EE
 dump ww_c4 $B/waterworld.o _ZN5madrl9ww_kernelIfLi4ELi1ELi30ELb0ELb0EEEvNS_8WWParamsIT_EE
-dump pe_c3 $B/pursuit.o _ZN5madrl9pe_kernelILi1ELi2ELi7ELb0EEEvNS_8PEParamsE
+dump pe_c3 $B/pursuit.o _ZN5madrl9pe_kernelILi1ELi2ELi7ELb0ELb1EEEvNS_8PEParamsE
 dump hw_c5 $B/hostage.o "$(cuobjdump -res-usage $B/hostage.o | grep -o '_ZN5madrl9hw_kernelIfLi1ELi1ELi30E[A-Za-z0-9_]*' | head -n 1)"
