@@ -72,6 +72,21 @@ __global__ void frame_stack_kernel(int T, size_t n /* E*A*D */, int AD, const fl
 // StandardizedEnv running estimates (__init__.py:241-270), in place over the time axis.
 //   mean <- (1-a) mean + a x ;  var <- (1-a) var + a (x - mean)^2 ;  out = (x - mean) / (sqrt(var) + eps)
 // center = 1 for observations; rewards are only divided (and scaled), never centred.
+// 1 / (sqrt(v) + eps) in float64 WITHOUT the DSQRT / DDIV sequences (each some two dozen FP64 instructions, which made
+// these streaming passes FP64-bound at 29 % of the HBM roofline): float32 seeds (MUFU.RSQ / MUFU.RCP, ~1e-7) refined by
+// one Newton step each in float64 (-> ~1e-14 relative; the result is rounded to float32 afterwards).  The running
+// mean / variance recurrences themselves stay exact float64.  v == 0 (or denormal) takes the exact path.
+__device__ __forceinline__ double inv_std(double v, double eps) {
+  const float vf = (float)v;
+  if (!(vf > 1e-30f) || !(vf < 1e30f)) return 1.0 / (sqrt(v) + eps);
+  double y = (double)rsqrtf(vf);
+  y = y * (1.5 - 0.5 * v * y * y);          // 1 / sqrt(v)
+  const double den = v * y + eps;           // sqrt(v) + eps
+  double r = (double)(1.0f / (float)den);
+  r = r * (2.0 - den * r);
+  return r;
+}
+
 __global__ void standardize_kernel(int T, size_t n, float* __restrict__ x, double* __restrict__ mean,
                                    double* __restrict__ var, double alpha, double eps, int center,
                                    double scale, int enable) {
@@ -86,7 +101,7 @@ __global__ void standardize_kernel(int T, size_t n, float* __restrict__ x, doubl
       m = (1.0 - alpha) * m + alpha * xv;
       const double d = xv - m;
       v = (1.0 - alpha) * v + alpha * d * d;
-      o = (center ? (xv - m) : xv) / (sqrt(v) + eps);
+      o = (center ? (xv - m) : xv) * inv_std(v, eps);
     }
     x[k] = (float)(scale * o);
   }
@@ -111,13 +126,13 @@ __global__ void standardize_terminal_kernel(int T, int E, size_t per_env, float*
       m = (1.0 - alpha) * m + alpha * tv;
       const double d = tv - m;
       v = (1.0 - alpha) * v + alpha * d * d;
-      term[k] = (float)((tv - m) / (sqrt(v) + eps));
+      term[k] = (float)((tv - m) * inv_std(v, eps));
     }
     const double xv = (double)x[k];
     m = (1.0 - alpha) * m + alpha * xv;
     const double d = xv - m;
     v = (1.0 - alpha) * v + alpha * d * d;
-    x[k] = (float)((xv - m) / (sqrt(v) + eps));
+    x[k] = (float)((xv - m) * inv_std(v, eps));
   }
   mean[i] = m;
   var[i] = v;
@@ -325,6 +340,23 @@ __global__ void paths_pack_kernel(int T, int E, int A, int D, const uint32_t* __
   for (int d = lane; d < D; d += 32) __stcs(out + d, __ldcs(in + d));
 }
 
+// Narrow rows (rewards, actions, infos: D <= 4 words): one THREAD per source row instead of one warp.
+__global__ void paths_pack_narrow_kernel(int T, int E, int A, int D, const uint32_t* __restrict__ src,
+                                         const uint32_t* __restrict__ first, const int32_t* __restrict__ seg_start,
+                                         const int32_t* __restrict__ seg_len, uint32_t* __restrict__ dst) {
+  const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // source row (t, e, a)
+  const size_t rows = (size_t)T * E * A;
+  if (row >= rows) return;
+  const int a = (int)(row % A);
+  const size_t te = row / A;
+  const int e = (int)(te % E), t = (int)(te / E);
+  const int s = seg_start[te], L = seg_len[te];
+  const uint32_t* in = first ? (t == 0 ? first + ((size_t)e * A + a) * D : src + (row - (size_t)E * A) * D)
+                             : src + row * D;
+  uint32_t* out = dst + ((size_t)e * T * A + (size_t)s * A + (size_t)a * L + (t - s)) * D;
+  for (int d = 0; d < D; ++d) out[d] = in[d];
+}
+
 }  // namespace madrl
 
 using namespace madrl;
@@ -436,10 +468,14 @@ extern "C" int madrl_paths_pack_u32(int T, int E, int A, int D, const void* src_
   MADRL_REQUIRE(T >= 1 && E >= 1 && A >= 1 && D >= 1, "bad shape");
   MADRL_REQUIRE(src_dev && seg_start_dev && seg_len_dev && dst_dev, "NULL pointer");
   const size_t rows = (size_t)T * E * A;
-  const size_t blocks = (rows * 32 + 255) / 256;
+  const size_t blocks = D <= 4 ? (rows + 255) / 256 : (rows * 32 + 255) / 256;
   MADRL_REQUIRE(blocks < ((size_t)1 << 31), "too many rows for one launch");
-  MADRL_LAUNCH(paths_pack_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, T, E, A, D, (const uint32_t*)src_dev,
-               (const uint32_t*)first_dev, seg_start_dev, seg_len_dev, (uint32_t*)dst_dev);
+  if (D <= 4)
+    MADRL_LAUNCH(paths_pack_narrow_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, T, E, A, D,
+                 (const uint32_t*)src_dev, (const uint32_t*)first_dev, seg_start_dev, seg_len_dev, (uint32_t*)dst_dev);
+  else
+    MADRL_LAUNCH(paths_pack_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, T, E, A, D, (const uint32_t*)src_dev,
+                 (const uint32_t*)first_dev, seg_start_dev, seg_len_dev, (uint32_t*)dst_dev);
   g_launches.fetch_add(1);
   MADRL_CUDA_CHECK(cudaGetLastError());
   return MADRL_OK;

@@ -173,6 +173,7 @@ static inline float fminf_(float a, float b) { return a < b ? a : b; }
 
 // ---- scalar intrinsics ---------------------------------------------------------------------------
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline float rsqrtf(float v) { return 1.0f / sqrtf(v); }
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {   // PRMT, default mode
   const uint64_t src = ((uint64_t)y << 32) | x;
   unsigned r = 0;
