@@ -1,5 +1,6 @@
-"""TEST INFRASTRUCTURE: run tests/test_emulated_kernels.py against AddressSanitizer / UBSan builds of
-the emulator library (kernel source + host launch code compiled by g++):
+"""TEST INFRASTRUCTURE: run tests/test_emulated_kernels.py and the emulated tests of tests/test_heuristics.py (the
+in-kernel policies, the generators) against AddressSanitizer / UBSan builds of the emulator library (kernel source +
+host launch code compiled by g++):
 
     python tests/emu/sanitize.py [address|undefined] [default|experiments]
 
@@ -24,7 +25,8 @@ lib = C.CDLL(%(lib)r)
 driver._declare(lib)
 driver._libs[tuple(sorted(T.VARIANTS[%(variant)r]))] = lib
 import pytest
-sys.exit(pytest.main([%(testfile)r, "-x", "-q", "-k", %(variant)r, "-p", "no:cacheprovider"]))
+sys.exit(pytest.main([%(testfile)r, %(heurfile)r, "-x", "-q", "-k", %(variant)r + " or policy or generator or closed_loop",
+                      "-p", "no:cacheprovider"]))
 '''
 
 
@@ -46,7 +48,8 @@ def main():
         raise SystemExit("no %s found" % rt)
     env["ASAN_OPTIONS"] = "detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1"
     code = CODE % dict(tests=os.path.join(ROOT, "tests"), root=ROOT, lib=lib, variant=variant,
-                       testfile=os.path.join(ROOT, "tests", "test_emulated_kernels.py"))
+                       testfile=os.path.join(ROOT, "tests", "test_emulated_kernels.py"),
+                       heurfile=os.path.join(ROOT, "tests", "test_heuristics.py"))
     return subprocess.call([sys.executable, "-c", code], env=env, cwd=ROOT)
 
 
